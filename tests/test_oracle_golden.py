@@ -1,0 +1,193 @@
+"""Pin the CPU oracle against golden vectors produced by the unmodified reference.
+
+(CPU only.)  The goldens come from tests/golden/make_golden.py.
+"""
+import hashlib
+import os
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import disgat as od
+from oracle import graph as og
+from helpers import load, t, assert_close, params_from, GOLDEN
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+# ------------------------------------------------------------------ graph construction
+def test_graph_edge_list_bit_exact():
+    g = load("graph_small")
+    n, r, c = og.edge_list_to_coo(g["el_edges"])
+    assert n == int(g["el_n"])
+    idx, val = og.build_adjacency(n, r, c)
+    assert np.array_equal(idx, g["el_indices"])
+    assert np.array_equal(val, g["el_values"])
+    assert np.array_equal(og.features_row_normalize(g["el_feat"]).astype(np.float32), g["el_features"])
+
+
+def test_graph_weighted_csr_bit_exact():
+    g = load("graph_small")
+    idx, val = og.build_adjacency(int(g["csr_n"]), g["csr_row"], g["csr_col"], g["csr_val"])
+    assert np.array_equal(idx, g["csr_indices"])
+    assert np.array_equal(val, g["csr_values"])
+
+
+@pytest.mark.parametrize("ds", ["cora", "chameleon", "cora_full"])
+def test_graph_bundled_hash(ds):
+    import scipy.sparse as sp
+    g = load("graph_bundled")
+    d = os.path.join(ROOT, "data", ds)
+    if os.path.exists(os.path.join(d, "adj_1.npy")):
+        n, r, c = og.edge_list_to_coo(np.load(os.path.join(d, "adj_1.npy")))
+        v = None
+    else:
+        m = sp.load_npz(os.path.join(d, "adj_1_sp.npz")).tocoo()
+        n, r, c, v = m.shape[0], m.row, m.col, m.data
+    idx, val = og.build_adjacency(n, r, c, v)
+    assert n == int(g[ds + "_n"]) and idx.shape[1] == int(g[ds + "_e"])
+    assert sha(idx) == str(g[ds + "_idx_sha"])
+    assert sha(val) == str(g[ds + "_val_sha"])
+
+
+def test_sampler_cora_bit_exact():
+    import scipy.sparse as sp
+    g = load("graph_bundled")
+    m = sp.load_npz(os.path.join(ROOT, "data", "cora", "adj_1_sp.npz")).tocoo()
+    idx, _ = og.build_adjacency(m.shape[0], m.row, m.col, m.data)
+    torch.manual_seed(4)
+    np.random.seed(4)
+    pairs, lab = og.sample_pairs(m.shape[0], idx, chunk_rows=677)
+    assert pairs.shape[1] == int(g["cora_sample_m"])
+    assert sha(pairs) == str(g["cora_sample_idx_sha"])
+    assert sha(lab) == str(g["cora_sample_lab_sha"])
+
+
+# ------------------------------------------------------------------ sparse ops / loss
+@pytest.mark.parametrize("tag", ["s8", "s64"])
+def test_sp_ops(tag):
+    g = load("layer_" + tag)
+    idx = t(g["indices"])
+    assert_close(od.sp_matmul(idx, t(g["spmm_vals"]), t(g["spmm_mat"])), g["spmm_out"], what="sp_matmul")
+    assert_close(od.sp_softmax(idx, t(g["spmm_vals"]), int(g["n"])), g["spsm_out"], what="sp_softmax")
+
+
+def test_adj_mse_loss():
+    g = load("loss_small")
+    assert_close(od.adj_mse_loss(t(g["pred"]), t(g["tgt"])), g["loss"], what="adj_mse_loss")
+
+
+# ------------------------------------------------------------------ one channel
+@pytest.mark.parametrize("tag", ["s8", "s64"])
+@pytest.mark.parametrize("att", [1, 2, 3])
+@pytest.mark.parametrize("gnn", ["AT", "SAGE", "GCN"])
+def test_layer_fwd_bwd(tag, att, gnn):
+    g = load("layer_" + tag)
+    k = "a%d_%s_" % (att, gnn)
+    p = {n_: v.clone().requires_grad_(True) for n_, v in params_from(g, k + "p.").items()}
+    x = t(g["x"]).clone().requires_grad_(True)
+    idx = t(g["indices"])
+    aux = [t(g["aux0"]), t(g["aux1"])]
+    out, e, au = od.disga_layer(p, "", x, idx, att, gnn, aux=aux)
+    assert_close(out, g[k + "out"], what="out")
+    assert_close(e, g[k + "edge_e"], what="edge_e")
+    assert_close(au[0], g[k + "aux0"], what="aux0")
+    assert_close(au[1], g[k + "aux1"], what="aux1")
+    loss = (out * t(g["r_out"])).sum() + (e * t(g["r_e"])).sum() \
+        + (au[0] * t(g["r_aux0"])).sum() + (au[1] * t(g["r_aux1"])).sum()
+    loss.backward()
+    assert_close(x.grad, g[k + "gx"], what="gx")
+    for name, prm in p.items():
+        if k + "g." + name in g:
+            assert_close(prm.grad, g[k + "g." + name], what="g." + name)
+        else:  # att=2: `a` receives no gradient in the reference
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ model traversal + losses
+MODEL_TAGS = ["model_a3_AT", "model_a1_SAGE", "model_a2_GCN", "model_a3_AT_res"]
+
+
+def model_setup(tag):
+    g = load(tag)
+    argv = [str(a) for a in g["argv"]]
+    att = int([a for a in argv if a.startswith("--att=")][0].split("=")[1])
+    gnn = [a for a in argv if a.startswith("--gnn_type=")][0].split("=")[1]
+    cfg = dict(nheads=4, att=att, gnn=gnn, residue="--residue" in argv,
+               residue_type=2 if "--residue_type=2" in argv else 0,
+               constrain_layer=1 if "--constrain_layer=1" in argv else 0)
+    return g, cfg
+
+
+def fusers_of(g, who):
+    return [params_from(g, "%s0.fuse1." % who), params_from(g, "%s0.fuse2." % who)]
+
+
+@pytest.mark.parametrize("tag", MODEL_TAGS)
+def test_model_traversal(tag):
+    g, cfg = model_setup(tag)
+    p = params_from(g, "enc0.")
+    x, idx = t(g["x"]), t(g["indices"])
+    aux = [t(g["aux0"]), t(g["aux1"])]
+    with torch.no_grad():
+        r = od.disgat_traverse(p, fusers_of(g, "cls"), x, idx, cfg["nheads"], cfg["att"], cfg["gnn"],
+                               aux=aux, residue=cfg["residue"], residue_type=cfg["residue_type"])
+    assert_close(r["feats"][0], g["get_em_1"], what="get_em[0]")
+    assert_close(r["feats"][1], g["get_em_2"], what="get_em[1]")
+    assert_close(r["logp"], g["forward"], what="forward")
+    for layer in range(2):
+        assert_close(torch.stack(r["edge_e"][layer]), g["get_adjs"][layer], what="get_adjs")
+        assert_close(torch.stack([h[0] for h in r["aux"][layer]]), g["pred_aux0"][layer], what="aux0")
+        assert_close(torch.stack([h[1] for h in r["aux"][layer]]), g["pred_aux1"][layer], what="aux1")
+        assert_close(torch.stack(r["edge_em"][layer]), g["edge_em_l%d" % layer], what="edge_em")
+
+
+def seed_all(s):
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+@pytest.mark.parametrize("tag", MODEL_TAGS)
+def test_sampler_small_bit_exact(tag):
+    g, cfg = model_setup(tag)
+    n, idx = int(g["n"]), g["indices"]
+    seed_all(8)
+    pairs, lab = og.sample_pairs(n, idx, chunk_rows=16)
+    assert np.array_equal(pairs, g["sup.sample_idx"])
+    assert np.array_equal(lab, g["sup.sample_lab"])
+    homo, het = og.homo_hetero_split(idx, g["labels"])
+    seed_all(9)
+    p0, l0 = og.sample_pairs(n, homo, chunk_rows=32)
+    p1, l1 = og.sample_pairs(n, het, chunk_rows=48)
+    assert np.array_equal(p0, g["dis.sample_idx0"]) and np.array_equal(l0, g["dis.sample_lab0"])
+    assert np.array_equal(p1, g["dis.sample_idx1"]) and np.array_equal(l1, g["dis.sample_lab1"])
+
+
+@pytest.mark.parametrize("tag", MODEL_TAGS[:1] + MODEL_TAGS[3:])
+def test_first_step_losses_and_grads(tag):
+    """CLS step (first in the recorded sequence, so the encoder is still enc0)."""
+    g, cfg = model_setup(tag)
+    p = {k: v.clone().requires_grad_(True) for k, v in params_from(g, "enc0.").items()}
+    fus = [{k: v.clone().requires_grad_(True) for k, v in f.items()} for f in fusers_of(g, "cls")]
+    mp = params_from(g, "cls0.classifier.")
+    x, idx, labels = t(g["x"]), t(g["indices"]), t(g["labels"])
+    r = od.disgat_traverse(p, fus, x, idx, cfg["nheads"], cfg["att"], cfg["gnn"],
+                           residue=cfg["residue"], residue_type=cfg["residue_type"])
+    logp = od.mlp(mp, r["feats"][-1], cls=True)
+    tr = t(g["cls_idx_train"])
+    loss = torch.nn.functional.nll_loss(logp[tr], labels[tr])
+    assert_close(loss, g["cls.log.loss_train"], rtol=1e-5, what="cls loss")
+    loss.backward()
+    for k, prm in p.items():
+        key = "cls.encgrad." + k
+        if key in g:
+            assert_close(prm.grad, g[key], rtol=2e-5, what=key)
+    for k, prm in fus[0].items():
+        assert_close(prm.grad, g["cls.fuse1grad." + k], rtol=2e-5, what="fuse1 " + k)
