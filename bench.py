@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py -- DISGAT fwd+bwd edges/s on B200 (the BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl edis|reference]
+
+One "step" = DISGAT.get_em forward + backward of a scalar loss, 2 layers x C channels, train
+mode (dropout on), on the synthetic power-law graph of BASELINE config[3] (2.4M nodes, ~62M
+edges, F=100, C=8, D=64, att=3, gnn_type=AT).  Prints ONE JSON line (rank 0).
+  value      edges/s with inputs resident in HBM (CUDA events, max over ranks)
+  e2e        same through the public API with the features coming from pinned HOST memory
+             every step (H2D inside the timed region) and the loss read back (D2H)
+  roofline   the dominant kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak
+  cpu_baseline  the CPU oracle port of the reference's path on a bounded sample of the workload
+`--impl reference` times that CPU port as the reference arm (no GPU work).
+Multi-GPU (torchrun, N > 1): destination-range partition of the graph, one rank per GPU, features
+all-gathered per layer and weight gradients all-reduced over NCCL (see DESIGN.md section e).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="edis", choices=["edis", "reference"])
+    ap.add_argument("--nodes", type=int, default=2_400_000)
+    ap.add_argument("--raw-edges", type=int, default=30_600_000, help="directed draws before symmetrise/dedup")
+    ap.add_argument("--feat", type=int, default=100)
+    ap.add_argument("--nhead", type=int, default=8)
+    ap.add_argument("--nhid", type=int, default=64)
+    ap.add_argument("--att", type=int, default=3)
+    ap.add_argument("--gnn_type", default="AT")
+    ap.add_argument("--dropout", type=float, default=0.1)
+    ap.add_argument("--cpu-nodes", type=int, default=12_000, help="CPU-baseline sample: nodes")
+    ap.add_argument("--cpu-raw-edges", type=int, default=150_000, help="CPU-baseline sample: raw edge draws")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--max-chunk", type=int, default=0)
+    return ap.parse_args()
+
+
+def model_args(a):
+    from edgedisentangle_ssl_b200.utils import get_parser
+    args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--att=%d" % a.att, "--gnn_type=" + a.gnn_type,
+                                    "--nhead=%d" % a.nhead, "--nhid=%d" % a.nhid, "--dropout=%g" % a.dropout])
+    args.size = a.feat
+    return args
+
+
+# ---------------------------------------------------------------------------------- CPU arm
+def cpu_port_rate(a, steps, warmup, threads):
+    """edges/s of the oracle port (oracle/disgat.py: the reference's per-channel eager path)."""
+    from oracle import disgat as od
+    from oracle import graph as og
+    from edgedisentangle_ssl_b200.synthetic import power_law_graph
+    torch.set_num_threads(threads)
+    idx = torch.from_numpy(power_law_graph(a.cpu_nodes, a.cpu_raw_edges, seed=1))
+    n, e = a.cpu_nodes, idx.shape[1]
+    gen = torch.Generator().manual_seed(0)
+    C, D, F = a.nhead, a.nhid, a.feat
+    p = {}
+    for layer, fin in ((1, F), (2, D)):
+        for c in range(C):
+            pre = "attention%d_%d." % (layer, c)
+            p[pre + "W"] = (torch.randn((2 * fin if a.att == 3 else fin), D, generator=gen) * 0.1).requires_grad_(True)
+            p[pre + "a"] = (torch.randn((D if a.att == 3 else 2 * D), 1, generator=gen) * 0.1).requires_grad_(True)
+            p[pre + "W_em"] = (torch.randn(fin, D, generator=gen) * 0.1).requires_grad_(True)
+    fus = [{"fuse.weight": (torch.randn(D, C * D, generator=gen) * 0.05).requires_grad_(True),
+            "fuse.bias": torch.zeros(D, requires_grad=True)} for _ in range(2)]
+    x = torch.randn(n, F, generator=gen)
+    R = torch.randn(n, D, generator=gen)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        r = od.disgat_traverse(p, fus, x, idx, C, a.att, a.gnn_type, dropout=a.dropout, training=True)
+        loss = (r["feats"][-1] * R).sum()
+        loss.backward()
+        for v in list(p.values()) + [w for f in fus for w in f.values()]:
+            v.grad = None
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    sec = float(np.mean(times))
+    return e / sec, sec, n, e
+
+
+def run_reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    rate, sec, n, e = cpu_port_rate(a, a.steps, a.warmup, threads)
+    sample = "oracle port, power-law sample n=%d E=%d (F=%d C=%d D=%d att=%d %s), %d steps" % (
+        n, e, a.feat, a.nhead, a.nhid, a.att, a.gnn_type, a.steps)
+    line = {
+        "impl": "reference", "metric": "DISGAT fwd+bwd edges/s", "value": rate, "unit": "edges/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, e_full=None),
+        "cpu_baseline": {"value": rate, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(a, e_full, extra=None):
+    cfg = {"workload": "synthetic power-law graph, ogbn-products shape (BASELINE config[3]): "
+                       "N=%d, raw draws=%d, F=%d, C=%d, D=%d, att=%d, gnn_type=%s, full-batch DISGAT.get_em fwd+bwd, "
+                       "train mode dropout=%g" % (a.nodes, a.raw_edges, a.feat, a.nhead, a.nhid, a.att, a.gnn_type,
+                                                 a.dropout),
+           "l2_policy": "inputs larger than L2 (node tensors are GBs; no flush needed)"}
+    if e_full is not None:
+        cfg["edges"] = int(e_full)
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+# ---------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            pass
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for nm, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------- GPU arm
+def algorithmic_bytes(n, e, C, D, att):
+    """SURVEY 8(d) gather model, per layer, fp32 (att 2/3; att 1 gathers scalars for the score)."""
+    cd = C * D
+    score = 4 * C if att == 1 else 4 * cd
+    fwd = e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n
+    bwd_dst = e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n
+    bwd_src = e * (score + 4 * cd) + 4 * cd * n
+    return {"disga_fwd": fwd, "disga_bwd_dst": bwd_dst, "disga_bwd_src": bwd_src}
+
+
+def main():
+    a = parse()
+    if a.impl == "reference":
+        return run_reference_arm(a)
+
+    import torch.distributed as dist
+    import edgedisentangle_ssl_b200 as edis
+    from edgedisentangle_ssl_b200 import functional as Fn
+    from edgedisentangle_ssl_b200.synthetic import power_law_graph
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the edis arm has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        from edgedisentangle_ssl_b200 import parallel as par
+
+    # ---- workload (weak scaling: every rank owns a graph of the same size) -------------------
+    t0 = time.time()
+    if world == 1:
+        idx = power_law_graph(a.nodes, a.raw_edges, seed=0)
+        graph = edis.Graph(a.nodes, idx[0], idx[1], device=dev, max_chunk=a.max_chunk)
+        n_local, n_total, e_local = a.nodes, a.nodes, graph.e
+        del idx
+    else:
+        n_total = a.nodes * world
+        part = par.build_partitioned_power_law(n_total, a.raw_edges * world, seed=0, rank=rank, world=world,
+                                                device=dev, max_chunk=a.max_chunk)
+        graph, n_local, e_local = part.graph, part.n_local, part.graph.e
+    setup_s = time.time() - t0
+
+    margs = model_args(a)
+    torch.manual_seed(4)
+    enc = edis.DISGAT(margs, nfeat=a.feat, nhid=a.nhid, nclass=a.nhid, nheads=a.nhead, dropout=a.dropout).to(dev)
+    fus = [edis.FuseLayer(margs, a.nhead, nfeat=a.nhid).to(dev), edis.FuseLayer(margs, a.nhead, nfeat=a.nhid).to(dev)]
+    enc.train()
+    params = [p for m in [enc] + fus for p in m.parameters()]
+    gen = torch.Generator().manual_seed(1234 + rank)
+    x_host = torch.randn(n_local, a.feat, generator=gen).pin_memory()
+    x_dev = x_host.to(dev)
+    R = torch.randn(n_local, a.nhid, device=dev)
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step(from_host):
+        if from_host:
+            x_dev.copy_(x_host, non_blocking=True)
+        if world == 1:
+            feats = enc.get_em(x_dev, graph, fus)
+        else:
+            feats = par.get_em_partitioned(enc, fus, x_dev, part)
+        loss = (feats[-1] * R).sum()
+        loss.backward()
+        if world > 1:
+            par.allreduce_grads(params)
+        if from_host:
+            loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+        for p in params:
+            p.grad = None
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(from_host, k):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(k):
+            step(from_host)
+        ev1.record()
+        barrier()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            tms = torch.tensor([ms], device=dev)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ms = float(tms.item())
+        return ms
+
+    for _ in range(max(a.warmup, 3)):
+        step(False)
+    clocks = ClockSampler(local)
+    clocks.start()
+    Fn.TIMER.reset()
+    Fn.TIMER.enabled = True
+    ms_res = timed(False, a.steps)
+    Fn.TIMER.enabled = False
+    kernel_ms = {k: float(np.mean(v)) for k, v in Fn.TIMER.durations_ms().items()}
+    launches = Fn.TIMER.launches
+    step(True)
+    ms_e2e = timed(True, a.steps)
+    clk = clocks.stop()
+
+    e_total = e_local
+    if world > 1:
+        te = torch.tensor([e_local], device=dev, dtype=torch.int64)
+        dist.all_reduce(te)
+        e_total = int(te.item())
+    value = e_total * a.steps / (ms_res * 1e-3)
+    e2e_value = e_total * a.steps / (ms_e2e * 1e-3)
+
+    # ---- roofline of the dominant kernel (rank 0's launches) ---------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    alg = algorithmic_bytes(graph.n, graph.e, a.nhead, a.nhid, a.att)
+    dom = max(kernel_ms, key=kernel_ms.get) if kernel_ms else None
+    roof = None
+    if dom:
+        ach = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
+                "kernel_ms": kernel_ms,
+                "all_kernels_gbs": {k: alg[k] / (v * 1e-3) / 1e9 for k, v in kernel_ms.items() if k in alg}}
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            roof["traffic"] = json.load(open(tpath)).get(dom)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu = None
+    if world == 1 and not a.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        rate, sec, cn, ce = cpu_port_rate(a, 2, 1, threads)
+        cpu = {"value": rate, "unit": "edges/s", "cores": threads, "kind": "port",
+               "sample": "oracle port on a power-law sample n=%d E=%d, same F/C/D/att/gnn, 2 steps of %.1f s"
+                         % (cn, ce, sec)}
+    line = {
+        "metric": "DISGAT fwd+bwd edges/s", "value": value, "unit": "edges/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_res / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, e_total, {"nodes_total": n_total, "setup_s": round(setup_s, 1),
+                                               "parallelism": "single GPU" if world == 1 else "dst-range x%d" % world,
+                                               "graph": graph.info}),
+        "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": ms_e2e / a.steps,
+                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4,
+                "note": "features from pinned host memory every step; graph handle resident (built once, like "
+                        "the reference's adj.cuda())"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

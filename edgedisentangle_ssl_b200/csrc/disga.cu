@@ -1,0 +1,873 @@
+// Fused DisGALayer kernels for sm_100a: all C channels of one DISGAT layer per launch.
+//
+// Replaces /root/reference/layers.py:349-416 (+ F.elu at 500/509), utils.py:192-207 and the
+// aggregation of SageConv / GraphConvolution (layers.py:96-110, 38-54), forward and backward.
+// HBM-bound gather / segment-reduce work: no tensor cores.  Scheduling:
+//   * persistent grid (multiple of the SM count), one warp per (row chunk, channel group);
+//   * rows longer than max_chunk are split into chunks whose partial sums go through a
+//     small partial buffer + combine kernel (power-law hubs do not serialise a warp);
+//   * per edge a warp gathers the source row with 128-bit coalesced loads (VecT) and reduces
+//     the per-channel dot products with warp shuffles over the D/4 lanes of a channel;
+//   * softmax is single pass: logits go through a sigmoid first (layers.py:392), so
+//     exp(sigmoid(e)) is in (1, e) and needs no running max;
+//   * backward = destination pass over CSR (dP, d logits) + source pass over CSC (dQ, dV):
+//     pull on both sides, no float atomics on node tensors, deterministic.
+// Template parameter RX selects the aggregated operand: RX == 0 -> per-channel V[N, C*D]
+// (gnn_type AT / GCN); RX > 0 -> the raw input X[N, F <= 32*RX] shared by all channels
+// (gnn_type SAGE), accumulated lane-strided.
+#include "edis_common.cuh"
+#include "traits.cuh"
+
+namespace edis {
+
+struct LayerArgs {
+  const Item* items;
+  int64_t n_units;          // items * G
+  int G;                    // channel groups per item
+  const int32_t* nbr;       // CSR col (dst pass / fwd) or CSC row (src pass)
+  const int32_t* eid;       // CSC -> CSR slot (src pass)
+  const float *P, *Q, *a, *V, *bias;   // V doubles as X[N, F] in SAGE mode
+  int64_t ldp, ldq, ldv;
+  int C, D, F;
+  // forward outputs / saved
+  float *out, *hpre, *edge_e, *stats;  // SAGE: hpre = neigh[N, C*F], out unused
+  // backward
+  const float *g_out, *g_edge_e;
+  float *gP, *gQ, *ga, *gV, *edge_rec, *gh;
+  int64_t ldgp, ldgq, ldgv;          // row strides of gP, gQ, gV
+  float* partial;
+  int64_t pwidth;
+  int training;
+  float p, inv_keep;
+  uint64_t seed;
+};
+
+template <int RX>
+__device__ __forceinline__ void load_x(float (&x)[RX > 0 ? RX : 1], const float* base, int lane, int F) {
+#pragma unroll
+  for (int k = 0; k < RX; ++k) x[k] = (k * 32 + lane < F) ? __ldg(base + k * 32 + lane) : 0.0f;
+}
+template <int RX>
+__device__ __forceinline__ void store_x(float* base, const float (&x)[RX > 0 ? RX : 1], int lane, int F) {
+#pragma unroll
+  for (int k = 0; k < RX; ++k)
+    if (k * 32 + lane < F) base[k * 32 + lane] = x[k];
+}
+
+// ------------------------------------------------------------------ forward
+template <class T, int ATT, int RX, int U>
+__global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
+  constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (; unit < A.n_units; unit += nwarps) {
+    const int64_t item_id = unit / A.G;
+    const int grp = static_cast<int>(unit - item_id * A.G);
+    const Item it = A.items[item_id];
+    const int c0 = grp * CPW;
+    const int off = c0 * A.D;
+    int cidx[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
+    float pr[R], ar[R], sd[NCH];
+    if (ATT >= 2) T::load(pr, A.P + static_cast<int64_t>(it.row) * A.ldp + off, lane, A.D);
+    if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
+    if (ATT == 1) {
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) sd[k] = __ldg(A.P + static_cast<int64_t>(it.row) * A.ldp + cidx[k]);
+    }
+    float acc[R], accx[NACC], ws[NCH], wms[NCH];
+    zero<T>(acc);
+#pragma unroll
+    for (int k = 0; k < NACC; ++k) accx[k] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) ws[k] = wms[k] = 0.0f;
+
+    for (int eb = it.beg; eb < it.end; eb += 32) {
+      const int cnt = min(32, it.end - eb);
+      const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
+      for (int t = 0; t < cnt; t += U) {
+        float q[U][R], h[U][R], qs[U][NCH], xj[U][RXA];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+            const int64_t j = __shfl_sync(FULL, myj, t + u);
+            if (ATT >= 2) T::load(q[u], A.Q + j * A.ldq + off, lane, A.D);
+            if (ATT == 1) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) qs[u][k] = __ldg(A.Q + j * A.ldq + cidx[k]);
+            }
+            if (RX == 0) T::load(h[u], A.V + j * A.ldv + off, lane, A.D);
+            else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+            const int64_t edge = eb + t + u;
+            float e[NCH];
+            if (ATT == 1) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) e[k] = sd[k] + qs[u][k];
+            } else {
+              float part[NCH];
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) part[k] = 0.0f;
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                if (ATT == 3) part[r / RPC] = fmaf(ar[r], lrelu01(pr[r] + q[u][r]), part[r / RPC]);
+                else part[r / RPC] = fmaf(pr[r], q[u][r], part[r / RPC]);
+              }
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) e[k] = T::reduce(part[k]);
+            }
+            float wm[NCH];
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const float w = __expf(sigmoidf_fast(e[k]));
+              const float ms = A.training ? keep_scale(A.seed, edge * A.C + cidx[k], A.p, A.inv_keep) : 1.0f;
+              wm[k] = w * ms;
+              ws[k] += w;
+              wms[k] += wm[k];
+            }
+            if (RX == 0) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) acc[r] = fmaf(wm[r / RPC], h[u][r], acc[r]);
+            } else {
+#pragma unroll
+              for (int cc = 0; cc < CPW; ++cc) {
+                const float wcc = T::bcast(wm, cc);
+#pragma unroll
+                for (int k = 0; k < RX; ++k) accx[cc * RXA + k] = fmaf(wcc, xj[u][k], accx[cc * RXA + k]);
+              }
+            }
+            if (T::writer(lane)) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) A.edge_e[edge * A.C + cidx[k]] = e[k];
+            }
+          }
+        }
+      }
+    }
+    const int64_t srow = static_cast<int64_t>(it.row);
+    if (RX == 0) {
+      if (it.slot < 0) {
+        float o[R], hp[R], br[R];
+        if (A.bias) T::load(br, A.bias + off, lane, A.D);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float wsum = ws[r / RPC];
+          float v = wsum > 0.0f ? acc[r] / wsum : 0.0f;
+          if (A.bias) v += br[r];
+          hp[r] = v;
+          o[r] = v > 0.0f ? v : expm1f(v);
+        }
+        T::store(A.hpre + srow * A.C * A.D + off, hp, lane, A.D);
+        T::store(A.out + srow * A.C * A.D + off, o, lane, A.D);
+      } else {
+        T::store(A.partial + static_cast<int64_t>(it.slot) * A.pwidth + off, acc, lane, A.D);
+      }
+    } else {
+      // SAGE: neigh = agg / (rowsum(alpha_drop) + 1) = acc / (sum w*mask + sum w)
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const float den = T::bcast(ws, cc) + T::bcast(wms, cc);
+        float o[RXA];
+#pragma unroll
+        for (int k = 0; k < RX; ++k)
+          o[k] = it.slot < 0 ? (den > 0.0f ? accx[cc * RXA + k] / den : 0.0f) : accx[cc * RXA + k];
+        float* dst = it.slot < 0 ? A.hpre + (srow * A.C + c0 + cc) * A.F
+                                 : A.partial + static_cast<int64_t>(it.slot) * A.pwidth + (c0 + cc) * A.F;
+        store_x<RX>(dst, o, lane, A.F);
+      }
+    }
+    if (T::writer(lane)) {
+      const int aggw = RX == 0 ? A.C * A.D : A.C * A.F;
+      float* st = it.slot < 0 ? A.stats + srow * 2 * A.C : A.partial + static_cast<int64_t>(it.slot) * A.pwidth + aggw;
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        st[cidx[k]] = ws[k];
+        st[A.C + cidx[k]] = wms[k];
+      }
+    }
+  }
+}
+
+// Split rows: sum the chunk partials, then the same epilogue.  One thread per (row, column).
+// W = width per channel (D, or F in SAGE mode).
+__global__ void k_combine_fwd(const SplitRow* split, int64_t n_split, const float* partial,
+                              int64_t pwidth, int C, int W, int sage, const float* bias, float* out,
+                              float* hpre, float* stats) {
+  const int CW = C * W;
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_split * CW) return;
+  const SplitRow s = split[idx / CW];
+  const int x = static_cast<int>(idx % CW);
+  const int c = x / W;
+  float acc = 0.0f, ws = 0.0f, wms = 0.0f, sx = 0.0f;
+  for (int k = 0; k < s.slot_cnt; ++k) {
+    const float* pb = partial + static_cast<int64_t>(s.slot_beg + k) * pwidth;
+    acc += pb[x];
+    ws += pb[CW + c];
+    wms += pb[CW + C + c];
+    if (x < 2 * C) sx += pb[CW + x];
+  }
+  const int64_t o = static_cast<int64_t>(s.row) * CW + x;
+  if (sage) {
+    const float den = ws + wms;
+    hpre[o] = den > 0.0f ? acc / den : 0.0f;
+  } else {
+    float v = ws > 0.0f ? acc / ws : 0.0f;
+    if (bias) v += bias[x];
+    hpre[o] = v;
+    out[o] = v > 0.0f ? v : expm1f(v);
+  }
+  if (x < 2 * C) stats[static_cast<int64_t>(s.row) * 2 * C + x] = sx;
+}
+
+// out[row*ld + x] = sum_slots partial[slot*pwidth + seg_off + x], x < seg_len
+__global__ void k_combine_rows(const SplitRow* split, int64_t n_split, const float* partial,
+                               int64_t pwidth, int seg_off, int seg_len, float* out, int64_t ld) {
+  const int64_t idx = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= n_split * seg_len) return;
+  const SplitRow s = split[idx / seg_len];
+  const int x = static_cast<int>(idx % seg_len);
+  float acc = 0.0f;
+  for (int k = 0; k < s.slot_cnt; ++k)
+    acc += partial[static_cast<int64_t>(s.slot_beg + k) * pwidth + seg_off + x];
+  out[static_cast<int64_t>(s.row) * ld + x] = acc;
+}
+
+// ------------------------------------------------------------------ backward, destination pass
+// Per row i: gh_i = grad wrt the aggregate (AT/GCN: g_out * elu'(hpre); SAGE: g_neigh / div);
+// t_c = <gh_i, agg_i>_c (== sum_k alpha_ik dalpha_ik); per edge: d alpha_drop = <gh_i, V_j>_c,
+// d logit = alpha (d alpha - t) * s(1-s) [+ g_edge_e]; accumulates dP_i (registers) and da
+// (registers, flushed with vector atomics once per warp).
+template <class T, int ATT, int RX, int U>
+__global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
+  constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  float da[R];
+  zero<T>(da);
+  int da_grp = -1;
+  const int CD = A.C * A.D;
+  for (; unit < A.n_units; unit += nwarps) {
+    const int64_t item_id = unit / A.G;
+    const int grp = static_cast<int>(unit - item_id * A.G);
+    const Item it = A.items[item_id];
+    const int c0 = grp * CPW;
+    const int off = c0 * A.D;
+    if (ATT == 3 && grp != da_grp) {
+      if (da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
+      zero<T>(da);
+      da_grp = grp;
+    }
+    int cidx[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
+    const int64_t srow = static_cast<int64_t>(it.row);
+    const int64_t rowoff = srow * CD + off;
+    // every chunk of a split row computes the same gh; the first chunk (or the only one) stores it
+    bool first_chunk = it.slot < 0;
+    if (it.slot >= 0) first_chunk = item_id == 0 || A.items[item_id - 1].row != it.row;
+    float dh[R], dhx[NACC], tc[NCH], inv[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) {
+      const float wsum = __ldg(A.stats + srow * 2 * A.C + cidx[k]);
+      inv[k] = wsum > 0.0f ? 1.0f / wsum : 0.0f;
+    }
+    if (RX == 0) {
+      float go[R], hp[R], br[R], tpart[NCH];
+      T::load(go, A.g_out + rowoff, lane, A.D);
+      T::load(hp, A.hpre + rowoff, lane, A.D);
+      if (A.bias) T::load(br, A.bias + off, lane, A.D);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) tpart[k] = 0.0f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        dh[r] = hp[r] > 0.0f ? go[r] : go[r] * expf(hp[r]);
+        const float agg = A.bias ? hp[r] - br[r] : hp[r];
+        tpart[r / RPC] = fmaf(dh[r], agg, tpart[r / RPC]);
+      }
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) tc[k] = T::reduce(tpart[k]);
+      if (first_chunk) T::store(A.gh + rowoff, dh, lane, A.D);
+    } else {
+      // SAGE: div = rowsum(alpha_drop) + 1 = (sum w*mask + sum w) / sum w, detached (layers.py:103)
+      float wmsv[NCH], wsv[NCH], tmine[NCH];
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        wsv[k] = __ldg(A.stats + srow * 2 * A.C + cidx[k]);
+        wmsv[k] = __ldg(A.stats + srow * 2 * A.C + A.C + cidx[k]);
+        tmine[k] = 0.0f;
+      }
+#pragma unroll
+      for (int cc = 0; cc < CPW; ++cc) {
+        const float wsc = T::bcast(wsv, cc), den = wsc + T::bcast(wmsv, cc);
+        const float rdiv = den > 0.0f ? wsc / den : 0.0f;   // 1 / div
+        float gn[RXA], ng[RXA], o[RXA];
+        load_x<RX>(gn, A.g_out + (srow * A.C + c0 + cc) * A.F, lane, A.F);
+        load_x<RX>(ng, A.hpre + (srow * A.C + c0 + cc) * A.F, lane, A.F);
+        float tp = 0.0f;
+#pragma unroll
+        for (int k = 0; k < RX; ++k) {
+          dhx[cc * RXA + k] = gn[k] * rdiv;
+          o[k] = dhx[cc * RXA + k];
+          tp = fmaf(gn[k], ng[k], tp);     // <g_agg, agg> = <g_neigh, neigh>
+        }
+        tp = warp_sum(tp);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k)
+          if (T::ch(k, lane) == cc) tmine[k] = tp;
+        if (first_chunk) store_x<RX>(A.gh + (srow * A.C + c0 + cc) * A.F, o, lane, A.F);
+      }
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) tc[k] = tmine[k];
+    }
+
+    float pr[R], ar[R], dP[R], dsd[NCH];
+    if (ATT >= 2) T::load(pr, A.P + srow * A.ldp + off, lane, A.D);
+    if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
+    zero<T>(dP);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) dsd[k] = 0.0f;
+
+    for (int eb = it.beg; eb < it.end; eb += 32) {
+      const int cnt = min(32, it.end - eb);
+      const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
+      for (int t = 0; t < cnt; t += U) {
+        float q[U][R], h[U][R], ev[U][NCH], gx[U][NCH], xj[U][RXA];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+            const int64_t j = __shfl_sync(FULL, myj, t + u);
+            const int64_t edge = eb + t + u;
+            if (ATT >= 2) T::load(q[u], A.Q + j * A.ldq + off, lane, A.D);
+            if (RX == 0) T::load(h[u], A.V + j * A.ldv + off, lane, A.D);
+            else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              ev[u][k] = __ldg(A.edge_e + edge * A.C + cidx[k]);
+              gx[u][k] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + cidx[k]) : 0.0f;
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+            const int64_t edge = eb + t + u;
+            float gdot[NCH];
+            if (RX == 0) {
+              float gpart[NCH];
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) gpart[k] = 0.0f;
+#pragma unroll
+              for (int r = 0; r < R; ++r) gpart[r / RPC] = fmaf(dh[r], h[u][r], gpart[r / RPC]);
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) gdot[k] = T::reduce(gpart[k]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) gdot[k] = 0.0f;
+#pragma unroll
+              for (int cc = 0; cc < CPW; ++cc) {
+                float gp = 0.0f;
+#pragma unroll
+                for (int k = 0; k < RX; ++k) gp = fmaf(dhx[cc * RXA + k], xj[u][k], gp);
+                gp = warp_sum(gp);
+#pragma unroll
+                for (int k = 0; k < NCH; ++k)
+                  if (T::ch(k, lane) == cc) gdot[k] = gp;
+              }
+            }
+            float de[NCH];
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              const float s = sigmoidf_fast(ev[u][k]);
+              const float alpha = __expf(s) * inv[k];
+              const float ms = A.training ? keep_scale(A.seed, edge * A.C + cidx[k], A.p, A.inv_keep) : 1.0f;
+              const float ds = alpha * (gdot[k] * ms - tc[k]);
+              de[k] = fmaf(ds, s * (1.0f - s), gx[u][k]);
+              if (T::writer(lane)) {
+                A.edge_rec[edge * 2 * A.C + cidx[k]] = alpha * ms;
+                A.edge_rec[edge * 2 * A.C + A.C + cidx[k]] = de[k];
+              }
+              if (ATT == 1) dsd[k] += de[k];
+            }
+            if (ATT == 3) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) {
+                const float z = pr[r] + q[u][r];
+                const float d = de[r / RPC];
+                dP[r] = fmaf(d * ar[r], z > 0.0f ? 1.0f : 0.01f, dP[r]);
+                da[r] = fmaf(d, lrelu01(z), da[r]);
+              }
+            } else if (ATT == 2) {
+#pragma unroll
+              for (int r = 0; r < R; ++r) dP[r] = fmaf(de[r / RPC], q[u][r], dP[r]);
+            }
+          }
+        }
+      }
+    }
+    if (it.slot < 0) {
+      if (ATT >= 2) T::store(A.gP + srow * A.ldgp + off, dP, lane, A.D);
+      if (ATT == 1 && T::writer(lane)) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) A.gP[srow * A.ldgp + cidx[k]] = dsd[k];
+      }
+    } else {
+      float* pb = A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
+      if (ATT >= 2) T::store(pb + off, dP, lane, A.D);
+      if (ATT == 1 && T::writer(lane)) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) pb[cidx[k]] = dsd[k];
+      }
+    }
+  }
+  if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
+}
+
+// ------------------------------------------------------------------ backward, source pass
+// Per source row j over its out-edges (CSC): dV_j = sum_i alpha_drop_ij gh_i (HASV),
+// dQ_j = sum_i d logit_ij * d e_ij / d Q_j.  Pull: gathers gh_i (and P_i), no atomics.
+template <class T, int ATT, bool HASV, int U>
+__global__ void __launch_bounds__(256) k_disga_bwd_src(const LayerArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int CD = A.C * A.D;
+  for (; unit < A.n_units; unit += nwarps) {
+    const int64_t item_id = unit / A.G;
+    const int grp = static_cast<int>(unit - item_id * A.G);
+    const Item it = A.items[item_id];
+    const int c0 = grp * CPW;
+    const int off = c0 * A.D;
+    int cidx[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
+    float qr[R], ar[R], accV[R], accQ[R], dss[NCH];
+    if (ATT == 3) {
+      T::load(qr, A.Q + static_cast<int64_t>(it.row) * A.ldq + off, lane, A.D);
+      T::load(ar, A.a + off, lane, A.D);
+    }
+    zero<T>(accV);
+    zero<T>(accQ);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) dss[k] = 0.0f;
+    for (int eb = it.beg; eb < it.end; eb += 32) {
+      const int cnt = min(32, it.end - eb);
+      const int myi = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
+      const int mye = lane < cnt ? __ldg(A.eid + eb + lane) : 0;
+      for (int t = 0; t < cnt; t += U) {
+        float pg[U][R], dh[U][R], ad[U][NCH], de[U][NCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+            const int64_t i = __shfl_sync(FULL, myi, t + u);
+            const int64_t edge = __shfl_sync(FULL, mye, t + u);
+            if (ATT >= 2) T::load(pg[u], A.P + i * A.ldp + off, lane, A.D);
+            if (HASV) T::load(dh[u], A.gh + i * CD + off, lane, A.D);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) {
+              if (HASV) ad[u][k] = __ldg(A.edge_rec + edge * 2 * A.C + cidx[k]);
+              de[u][k] = __ldg(A.edge_rec + edge * 2 * A.C + A.C + cidx[k]);
+            }
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u < cnt) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+              if (HASV) accV[r] = fmaf(ad[u][r / RPC], dh[u][r], accV[r]);
+              if (ATT == 3) {
+                const float z = pg[u][r] + qr[r];
+                accQ[r] = fmaf(de[u][r / RPC] * ar[r], z > 0.0f ? 1.0f : 0.01f, accQ[r]);
+              } else if (ATT == 2) {
+                accQ[r] = fmaf(de[u][r / RPC], pg[u][r], accQ[r]);
+              }
+            }
+            if (ATT == 1) {
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) dss[k] += de[u][k];
+            }
+          }
+        }
+      }
+    }
+    const int64_t rowoff = static_cast<int64_t>(it.row) * CD + off;
+    if (it.slot < 0) {
+      if (HASV) T::store(A.gV + static_cast<int64_t>(it.row) * A.ldgv + off, accV, lane, A.D);
+      if (ATT >= 2) T::store(A.gQ + static_cast<int64_t>(it.row) * A.ldgq + off, accQ, lane, A.D);
+      if (ATT == 1 && T::writer(lane)) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) A.gQ[static_cast<int64_t>(it.row) * A.ldgq + cidx[k]] = dss[k];
+      }
+    } else {
+      float* pb = A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
+      if (HASV) T::store(pb + off, accV, lane, A.D);
+      if (ATT >= 2) T::store(pb + CD + off, accQ, lane, A.D);
+      if (ATT == 1 && T::writer(lane)) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) pb[CD + cidx[k]] = dss[k];
+      }
+    }
+  }
+}
+
+// SAGE: gX_j = sum_i sum_c alpha_drop_ij^c gh_i^c.  One warp per source-row chunk, all channels.
+template <int RX>
+__global__ void __launch_bounds__(256) k_sage_bwd_src_x(const LayerArgs A) {
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  for (; unit < A.n_units; unit += nwarps) {
+    const Item it = A.items[unit];
+    float acc[RX];
+#pragma unroll
+    for (int k = 0; k < RX; ++k) acc[k] = 0.0f;
+    for (int eb = it.beg; eb < it.end; eb += 32) {
+      const int cnt = min(32, it.end - eb);
+      const int myi = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
+      const int mye = lane < cnt ? __ldg(A.eid + eb + lane) : 0;
+      for (int t = 0; t < cnt; ++t) {
+        const int64_t i = __shfl_sync(FULL, myi, t);
+        const int64_t edge = __shfl_sync(FULL, mye, t);
+        for (int c = 0; c < A.C; ++c) {
+          const float ad = __ldg(A.edge_rec + edge * 2 * A.C + c);
+          float g[RX];
+          load_x<RX>(g, A.gh + (i * A.C + c) * A.F, lane, A.F);
+#pragma unroll
+          for (int k = 0; k < RX; ++k) acc[k] = fmaf(ad, g[k], acc[k]);
+        }
+      }
+    }
+    float* dst = it.slot < 0 ? A.gV + static_cast<int64_t>(it.row) * A.F
+                             : A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
+    store_x<RX>(dst, acc, lane, A.F);
+  }
+}
+
+// ------------------------------------------------------------------ host dispatch
+enum class Pass { Fwd, BwdDst, BwdSrc };
+
+template <class K>
+static int launch_persistent(K kernel, const edis_graph* g, const LayerArgs& A, cudaStream_t st) {
+  if (A.n_units == 0) return EDIS_OK;
+  int blocks = launch_grid(reinterpret_cast<const void*>(kernel), 256, 0, g->sm_count);
+  const int64_t need = (A.n_units + 7) / 8;
+  if (need < blocks) blocks = static_cast<int>(need);
+  kernel<<<blocks, 256, 0, st>>>(A);
+  EDIS_CUDA(cudaGetLastError());
+  return EDIS_OK;
+}
+
+template <class T, int ATT, int RX, int U>
+static int launch_pass(Pass pass, const edis_graph* g, LayerArgs A, cudaStream_t st) {
+  A.G = A.C / T::CPW;
+  const Schedule& s = pass == Pass::BwdSrc ? g->src : g->dst;
+  A.items = s.items;
+  A.n_units = s.n_items * A.G;
+  if (pass == Pass::Fwd) return launch_persistent(&k_disga_fwd<T, ATT, RX, U>, g, A, st);
+  if (pass == Pass::BwdDst) return launch_persistent(&k_disga_bwd_dst<T, ATT, RX, U>, g, A, st);
+  if (RX == 0) return launch_persistent(&k_disga_bwd_src<T, ATT, true, U>, g, A, st);
+  return launch_persistent(&k_disga_bwd_src<T, ATT, false, 4>, g, A, st);
+}
+
+template <class T, int RX, int U>
+static int launch_att(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
+  switch (att) {
+    case 1: return launch_pass<T, 1, RX, U>(pass, g, A, st);
+    case 2: return launch_pass<T, 2, RX, U>(pass, g, A, st);
+    case 3: return launch_pass<T, 3, RX, U>(pass, g, A, st);
+  }
+  set_error("att must be 1, 2 or 3 (got %d)", att);
+  return EDIS_ERR_ARG;
+}
+
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
+// Layout choice: D == 64 and even C -> 128-bit path (2 or 4 channels per warp); other shapes ->
+// lane-strided scalar path (still CUDA; covers any C and D <= 256).
+static int launch_layer(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
+  const int C = A.C, D = A.D;
+  static const int kv_env = env_int("EDIS_KV", 0);
+  if (D == 64 && C % 2 == 0) {
+    int kv = kv_env ? kv_env : (C % 4 == 0 ? 2 : 1);
+    if (kv == 4 && C % 8 == 0) return launch_att<VecT<4, 16>, 0, 1>(pass, g, A, att, st);
+    if (kv >= 2 && C % 4 == 0) return launch_att<VecT<2, 16>, 0, 2>(pass, g, A, att, st);
+    return launch_att<VecT<1, 16>, 0, 4>(pass, g, A, att, st);
+  }
+  if (D == 32 && C % 4 == 0) return launch_att<VecT<1, 8>, 0, 4>(pass, g, A, att, st);
+  if (D == 128) return launch_att<VecT<1, 32>, 0, 4>(pass, g, A, att, st);
+  if (D <= 32) return launch_att<ScaT<1>, 0, 4>(pass, g, A, att, st);
+  if (D <= 64) return launch_att<ScaT<2>, 0, 4>(pass, g, A, att, st);
+  if (D <= 128) return launch_att<ScaT<4>, 0, 2>(pass, g, A, att, st);
+  if (D <= 256) return launch_att<ScaT<8>, 0, 1>(pass, g, A, att, st);
+  set_error("unsupported channel width D=%d (max 256)", D);
+  return EDIS_ERR_UNSUPPORTED;
+}
+
+template <class T>
+static int launch_sage_rx(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
+  if (A.F <= 64) return launch_att<T, 2, 2>(pass, g, A, att, st);
+  if (A.F <= 128) return launch_att<T, 4, 2>(pass, g, A, att, st);
+  if (A.F <= 256) return launch_att<T, 8, 1>(pass, g, A, att, st);
+  set_error("unsupported SAGE input width F=%d (max 256)", A.F);
+  return EDIS_ERR_UNSUPPORTED;
+}
+
+static int launch_sage(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
+  const int C = A.C, D = A.D;
+  if (D == 64 && C % 2 == 0) return launch_sage_rx<VecT<1, 16>>(pass, g, A, att, st);
+  if (D <= 64) return launch_sage_rx<ScaT<2>>(pass, g, A, att, st);
+  if (D <= 256) return launch_sage_rx<ScaT<8>>(pass, g, A, att, st);
+  set_error("unsupported channel width D=%d (max 256)", D);
+  return EDIS_ERR_UNSUPPORTED;
+}
+
+static int check_desc(const edis_layer_desc* d, const char* who) {
+  EDIS_CHECK_ARG(d, "%s: null descriptor", who);
+  EDIS_CHECK_ARG(d->att >= 1 && d->att <= 3, "%s: att=%d", who, d->att);
+  EDIS_CHECK_ARG(d->C >= 1 && d->D >= 2, "%s: C=%d D=%d", who, d->C, d->D);
+  EDIS_CHECK_ARG(!d->training || (d->p >= 0.0f && d->p < 1.0f), "%s: dropout p=%f", who, d->p);
+  return EDIS_OK;
+}
+
+static bool vec_ok(const void* p, int64_t ld) {
+  // the 128-bit path needs 16-byte aligned rows
+  return (reinterpret_cast<uintptr_t>(p) % 16 == 0) && (ld % 4 == 0);
+}
+
+static void fill_common(LayerArgs& A, const edis_layer_desc* d, const float* P, int64_t ldp,
+                        const float* Q, int64_t ldq, const float* a, const float* V, int64_t ldv,
+                        void* workspace) {
+  A.P = P; A.Q = Q; A.a = a; A.V = V;
+  A.ldp = ldp; A.ldq = ldq; A.ldv = ldv;
+  A.C = d->C; A.D = d->D; A.F = d->Dv;
+  A.partial = static_cast<float*>(workspace);
+  A.training = d->training && d->p > 0.0f;
+  A.p = d->p;
+  A.inv_keep = 1.0f / (1.0f - d->p);
+  A.seed = d->seed;
+}
+
+static int check_ws(const edis_graph* g, int64_t pw, void* workspace, int64_t bytes, const char* who) {
+  if ((g->dst.n_slots > 0 || g->src.n_slots > 0) &&
+      (!workspace || bytes < edis_graph_workspace_bytes(g, pw))) {
+    set_error("%s: workspace too small (%lld < %lld)", who, (long long)bytes,
+              (long long)edis_graph_workspace_bytes(g, pw));
+    return EDIS_ERR_WORKSPACE;
+  }
+  return EDIS_OK;
+}
+
+static unsigned nblk(int64_t total) { return static_cast<unsigned>((total + 255) / 256); }
+
+// shared tail of the two backward entry points: score-side source pass + combines
+static int bwd_score_src(const edis_graph* g, const edis_layer_desc* d, LayerArgs& A, bool sage,
+                         float* gQ, float* gV, cudaStream_t st) {
+  const int CD = d->C * d->D;
+  A.nbr = g->cscrow;
+  A.eid = g->csceid;
+  int rc = sage ? launch_sage(Pass::BwdSrc, g, A, d->att, st) : launch_layer(Pass::BwdSrc, g, A, d->att, st);
+  if (rc) return rc;
+  if (g->src.n_split > 0) {
+    if (!sage) {
+      k_combine_rows<<<nblk(g->src.n_split * CD), 256, 0, st>>>(g->src.split, g->src.n_split, A.partial,
+                                                               A.pwidth, 0, CD, gV, A.ldgv);
+    }
+    const int seg = d->att == 1 ? d->C : CD;
+    k_combine_rows<<<nblk(g->src.n_split * seg), 256, 0, st>>>(g->src.split, g->src.n_split, A.partial,
+                                                              A.pwidth, CD, seg, gQ, A.ldgq);
+    EDIS_CUDA(cudaGetLastError());
+  }
+  return EDIS_OK;
+}
+
+}  // namespace edis
+
+using namespace edis;
+
+extern "C" int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
+                              int64_t ldp, const float* Q, int64_t ldq, const float* a,
+                              const float* V, int64_t ldv, const float* bias, float* out,
+                              float* hpre, float* edge_e, float* stats, void* workspace,
+                              int64_t workspace_bytes, void* stream) {
+  int rc = check_desc(d, "edis_disga_fwd");
+  if (rc) return rc;
+  EDIS_CHECK_ARG(g && P && Q && V && out && hpre && edge_e && stats, "edis_disga_fwd: null pointer");
+  EDIS_CHECK_ARG(d->Dv == d->D, "edis_disga_fwd: Dv (%d) must equal D (%d)", d->Dv, d->D);
+  EDIS_CHECK_ARG(d->att != 3 || a, "edis_disga_fwd: att=3 needs a[C,D]");
+  EDIS_CHECK_ARG(d->D % 4 != 0 || (vec_ok(V, ldv) && (d->att == 1 || (vec_ok(P, ldp) && vec_ok(Q, ldq))) &&
+                                   vec_ok(out, 4) && vec_ok(hpre, 4)),
+                 "edis_disga_fwd: node tensors must be 16-byte aligned with ld %% 4 == 0");
+  const int64_t pw = static_cast<int64_t>(d->C) * d->D + 2 * d->C;
+  if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_fwd"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LayerArgs A = {};
+  fill_common(A, d, P, ldp, Q, ldq, a, V, ldv, workspace);
+  A.nbr = g->col;
+  A.bias = bias;
+  A.out = out; A.hpre = hpre; A.edge_e = edge_e; A.stats = stats;
+  A.pwidth = pw;
+  rc = launch_layer(Pass::Fwd, g, A, d->att, st);
+  if (rc) return rc;
+  if (g->dst.n_split > 0) {
+    k_combine_fwd<<<nblk(g->dst.n_split * d->C * d->D), 256, 0, st>>>(
+        g->dst.split, g->dst.n_split, A.partial, pw, d->C, d->D, 0, bias, out, hpre, stats);
+    EDIS_CUDA(cudaGetLastError());
+  }
+  return EDIS_OK;
+}
+
+static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc* d, const float* P,
+                              int64_t ldp, const float* Q, int64_t ldq, const float* a,
+                              const float* V, int64_t ldv, const float* bias, const float* hpre,
+                              const float* edge_e, const float* stats, const float* g_out,
+                              const float* g_edge_e, float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gV, int64_t ldgv,
+                              float* edge_rec, float* gh, void* workspace, int64_t workspace_bytes,
+                              void* stream) {
+  int rc = check_desc(d, "edis_disga_bwd");
+  if (rc) return rc;
+  EDIS_CHECK_ARG(g && P && Q && V && hpre && edge_e && stats && g_out && gP && gQ && gV && edge_rec && gh,
+                 "edis_disga_bwd: null pointer");
+  EDIS_CHECK_ARG(d->Dv == d->D, "edis_disga_bwd: Dv must equal D");
+  EDIS_CHECK_ARG(d->att != 3 || (a && ga), "edis_disga_bwd: att=3 needs a and ga");
+  EDIS_CHECK_ARG(d->D % 4 != 0 || (vec_ok(V, ldv) && (d->att == 1 || (vec_ok(P, ldp) && vec_ok(Q, ldq))) &&
+                                   vec_ok(g_out, 4) && vec_ok(gV, ldgv) && vec_ok(gh, 4) &&
+                                   (d->att == 1 || (vec_ok(gP, ldgp) && vec_ok(gQ, ldgq)))),
+                 "edis_disga_bwd: node tensors must be 16-byte aligned with ld %% 4 == 0");
+  const int CD = d->C * d->D;
+  const int64_t pw = 2 * static_cast<int64_t>(CD) + 2 * d->C;
+  if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_bwd"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LayerArgs A = {};
+  fill_common(A, d, P, ldp, Q, ldq, a, V, ldv, workspace);
+  A.bias = bias;
+  A.hpre = const_cast<float*>(hpre); A.edge_e = const_cast<float*>(edge_e); A.stats = const_cast<float*>(stats);
+  A.g_out = g_out; A.g_edge_e = g_edge_e;
+  A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gV; A.edge_rec = edge_rec; A.gh = gh;
+  A.ldgp = ldgp; A.ldgq = ldgq; A.ldgv = ldgv;
+  A.pwidth = pw;
+  if (phases & 1) {
+    A.nbr = g->col;
+    rc = launch_layer(Pass::BwdDst, g, A, d->att, st);
+    if (rc) return rc;
+    if (g->dst.n_split > 0) {
+      const int seg = d->att == 1 ? d->C : CD;
+      k_combine_rows<<<nblk(g->dst.n_split * seg), 256, 0, st>>>(g->dst.split, g->dst.n_split, A.partial, pw,
+                                                                0, seg, gP, A.ldgp);
+      EDIS_CUDA(cudaGetLastError());
+    }
+  }
+  if (phases & 2) return bwd_score_src(g, d, A, false, gQ, gV, st);
+  return EDIS_OK;
+}
+
+#define EDIS_BWD_ARGS                                                                               \
+  const edis_graph *g, const edis_layer_desc *d, const float *P, int64_t ldp, const float *Q,       \
+      int64_t ldq, const float *a, const float *V, int64_t ldv, const float *bias,                  \
+      const float *hpre, const float *edge_e, const float *stats, const float *g_out,               \
+      const float *g_edge_e, float *gP, int64_t ldgp, float *gQ, int64_t ldgq, float *ga,         \
+      float *gV, int64_t ldgv, float *edge_rec,                                                     \
+      float *gh, void *workspace, int64_t workspace_bytes, void *stream
+#define EDIS_BWD_PASS                                                                               \
+  g, d, P, ldp, Q, ldq, a, V, ldv, bias, hpre, edge_e, stats, g_out, g_edge_e, gP, ldgp, gQ, ldgq, ga, gV, ldgv, \
+      edge_rec, gh, workspace, workspace_bytes, stream
+
+extern "C" int edis_disga_bwd(EDIS_BWD_ARGS) { return disga_bwd_impl(3, EDIS_BWD_PASS); }
+extern "C" int edis_disga_bwd_dst(EDIS_BWD_ARGS) { return disga_bwd_impl(1, EDIS_BWD_PASS); }
+extern "C" int edis_disga_bwd_src(EDIS_BWD_ARGS) { return disga_bwd_impl(2, EDIS_BWD_PASS); }
+
+
+
+extern "C" int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
+                                   int64_t ldp, const float* Q, int64_t ldq, const float* a,
+                                   const float* X, int64_t ldx, float* neigh, float* edge_e,
+                                   float* stats, void* workspace, int64_t workspace_bytes,
+                                   void* stream) {
+  int rc = check_desc(d, "edis_disga_sage_fwd");
+  if (rc) return rc;
+  EDIS_CHECK_ARG(g && P && Q && X && neigh && edge_e && stats, "edis_disga_sage_fwd: null pointer");
+  EDIS_CHECK_ARG(d->Dv >= 1 && d->Dv <= 256, "edis_disga_sage_fwd: F=%d (Dv) must be in [1, 256]", d->Dv);
+  EDIS_CHECK_ARG(d->att != 3 || a, "edis_disga_sage_fwd: att=3 needs a[C,D]");
+  EDIS_CHECK_ARG(d->att == 1 || d->D % 4 != 0 || (vec_ok(P, ldp) && vec_ok(Q, ldq)),
+                 "edis_disga_sage_fwd: score operands must be 16-byte aligned with ld %% 4 == 0");
+  const int64_t pw = static_cast<int64_t>(d->C) * d->Dv + 2 * d->C;
+  if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_sage_fwd"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LayerArgs A = {};
+  fill_common(A, d, P, ldp, Q, ldq, a, X, ldx, workspace);
+  A.nbr = g->col;
+  A.hpre = neigh; A.edge_e = edge_e; A.stats = stats;
+  A.pwidth = pw;
+  rc = launch_sage(Pass::Fwd, g, A, d->att, st);
+  if (rc) return rc;
+  if (g->dst.n_split > 0) {
+    k_combine_fwd<<<nblk(g->dst.n_split * d->C * d->Dv), 256, 0, st>>>(
+        g->dst.split, g->dst.n_split, A.partial, pw, d->C, d->Dv, 1, nullptr, nullptr, neigh, stats);
+    EDIS_CUDA(cudaGetLastError());
+  }
+  return EDIS_OK;
+}
+
+extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
+                                   int64_t ldp, const float* Q, int64_t ldq, const float* a,
+                                   const float* X, int64_t ldx, const float* neigh,
+                                   const float* edge_e, const float* stats, const float* g_neigh,
+                                   const float* g_edge_e, float* gP, float* gQ, float* ga, float* gX,
+                                   float* edge_rec, float* gh, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
+  int rc = check_desc(d, "edis_disga_sage_bwd");
+  if (rc) return rc;
+  EDIS_CHECK_ARG(g && P && Q && X && neigh && edge_e && stats && g_neigh && gP && gQ && gX && edge_rec && gh,
+                 "edis_disga_sage_bwd: null pointer");
+  EDIS_CHECK_ARG(d->Dv >= 1 && d->Dv <= 256, "edis_disga_sage_bwd: F=%d (Dv) must be in [1, 256]", d->Dv);
+  EDIS_CHECK_ARG(d->att != 3 || (a && ga), "edis_disga_sage_bwd: att=3 needs a and ga");
+  const int CD = d->C * d->D;
+  const int64_t pw = 2 * static_cast<int64_t>(CD) + 2 * d->C + d->Dv;
+  if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_sage_bwd"))) return rc;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LayerArgs A = {};
+  fill_common(A, d, P, ldp, Q, ldq, a, X, ldx, workspace);
+  A.hpre = const_cast<float*>(neigh); A.edge_e = const_cast<float*>(edge_e); A.stats = const_cast<float*>(stats);
+  A.g_out = g_neigh; A.g_edge_e = g_edge_e;
+  A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gX; A.edge_rec = edge_rec; A.gh = gh;
+  A.ldgp = A.ldgq = d->att == 1 ? d->C : CD; A.ldgv = d->Dv;
+  A.pwidth = pw;
+  A.nbr = g->col;
+  rc = launch_sage(Pass::BwdDst, g, A, d->att, st);
+  if (rc) return rc;
+  if (g->dst.n_split > 0) {
+    const int seg = d->att == 1 ? d->C : CD;
+    k_combine_rows<<<nblk(g->dst.n_split * seg), 256, 0, st>>>(g->dst.split, g->dst.n_split, A.partial, pw,
+                                                              0, seg, gP, seg);
+    EDIS_CUDA(cudaGetLastError());
+  }
+  rc = bwd_score_src(g, d, A, true, gQ, nullptr, st);
+  if (rc) return rc;
+  // gX: one warp per source-row chunk, all channels
+  A.items = g->src.items;
+  A.n_units = g->src.n_items;
+  A.G = 1;
+  if (d->Dv <= 64) rc = launch_persistent(&k_sage_bwd_src_x<2>, g, A, st);
+  else if (d->Dv <= 128) rc = launch_persistent(&k_sage_bwd_src_x<4>, g, A, st);
+  else rc = launch_persistent(&k_sage_bwd_src_x<8>, g, A, st);
+  if (rc) return rc;
+  if (g->src.n_split > 0) {
+    k_combine_rows<<<nblk(g->src.n_split * d->Dv), 256, 0, st>>>(g->src.split, g->src.n_split, A.partial, pw,
+                                                                0, d->Dv, gX, d->Dv);
+    EDIS_CUDA(cudaGetLastError());
+  }
+  return EDIS_OK;
+}

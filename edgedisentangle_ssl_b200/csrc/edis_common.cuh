@@ -1,0 +1,106 @@
+// Shared helpers for libedis (sm_100a).  Not part of the public ABI (see include/edis.h).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "edis.h"
+
+namespace edis {
+
+void set_error(const char* fmt, ...);
+
+#define EDIS_CHECK_ARG(cond, ...)          \
+  do {                                     \
+    if (!(cond)) {                         \
+      ::edis::set_error(__VA_ARGS__);      \
+      return EDIS_ERR_ARG;                 \
+    }                                      \
+  } while (0)
+
+#define EDIS_CUDA(call)                                                                  \
+  do {                                                                                   \
+    cudaError_t err__ = (call);                                                          \
+    if (err__ != cudaSuccess) {                                                          \
+      ::edis::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                        cudaGetErrorString(err__));                                      \
+      return EDIS_ERR_CUDA;                                                              \
+    }                                                                                    \
+  } while (0)
+
+// One unit of row work: edges [beg, end) of `row`; slot < 0 when the chunk is the whole row,
+// else the index of its partial-result slot (rows longer than max_chunk are split).
+struct Item {
+  int32_t row, beg, end, slot;
+};
+struct SplitRow {
+  int32_t row, slot_beg, slot_cnt, pad;
+};
+
+struct Schedule {
+  Item* items = nullptr;        // device
+  SplitRow* split = nullptr;    // device
+  int64_t n_items = 0, n_slots = 0, n_split = 0;
+};
+
+}  // namespace edis
+
+struct edis_graph {
+  int64_t n = 0, e = 0, e_in = 0;
+  int device = 0;
+  int sm_count = 148;
+  int64_t max_in = 0, max_out = 0;
+  bool was_sorted = true;
+  // device arrays
+  int64_t* rowptr = nullptr;   // [n+1]
+  int32_t* col = nullptr;      // [e]   source of CSR slot k
+  int64_t* cscptr = nullptr;   // [n+1]
+  int32_t* cscrow = nullptr;   // [e]   destination of CSC slot k
+  int32_t* csceid = nullptr;   // [e]   CSR slot of CSC slot k
+  edis::Schedule dst, src;
+  // host mirrors (export / tests)
+  int64_t* h_rowptr = nullptr;
+  int32_t* h_col = nullptr;
+  int64_t* h_perm = nullptr;
+  int64_t* h_cscptr = nullptr;
+  int32_t* h_cscrow = nullptr;
+  int32_t* h_csceid = nullptr;
+};
+
+namespace edis {
+
+// ------------------------------------------------------------------ device helpers
+__device__ __forceinline__ float4 ldg4(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+__device__ __forceinline__ float sigmoidf_fast(float x) {
+  return __fdividef(1.0f, 1.0f + __expf(-x));
+}
+__device__ __forceinline__ float lrelu01(float z) { return fmaxf(z, 0.01f * z); }
+
+// Counter-based dropout mask: murmur3-style finaliser over (seed, element index).  Train-mode
+// parity with the reference is "within seed noise" (its CPU and CUDA streams already differ),
+// so the generator only has to be uniform and reproducible between fwd and bwd.
+__device__ __forceinline__ float keep_scale(uint64_t seed, uint64_t idx, float p, float inv_keep) {
+  uint32_t x = static_cast<uint32_t>(idx) ^ static_cast<uint32_t>(seed);
+  x *= 0x9E3779B1u;
+  x ^= static_cast<uint32_t>(idx >> 32) * 0x85EBCA77u + static_cast<uint32_t>(seed >> 32);
+  x ^= x >> 16;
+  x *= 0x85EBCA6Bu;
+  x ^= x >> 13;
+  x *= 0xC2B2AE35u;
+  x ^= x >> 16;
+  const float u = static_cast<float>(x >> 8) * (1.0f / 16777216.0f);
+  return u >= p ? inv_keep : 0.0f;
+}
+
+__device__ __forceinline__ void red_add4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+int launch_grid(const void* kernel, int block, size_t smem, int sm_count);
+
+}  // namespace edis

@@ -1,0 +1,336 @@
+// Host-side graph builder + device graph handle (CSR / CSC / chunked work schedules).
+// Integer work: must be bit-exact against the reference's `load_data` pipeline
+// (/root/reference/data_load.py:39-77, utils.py:163-170) -- see include/edis.h.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstring>
+#include <numeric>
+#include <vector>
+
+#include "edis_common.cuh"
+
+namespace edis {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+}
+
+int launch_grid(const void* kernel, int block, size_t smem, int sm_count) {
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, block, smem) != cudaSuccess ||
+      per_sm < 1)
+    per_sm = 1;
+  return per_sm * sm_count;
+}
+
+// Stable counting sort of `len` records by key[] in [0, n): fills order[] with source indices.
+static void counting_order(int64_t n, int64_t len, const int64_t* key, const int64_t* src_order,
+                           int64_t* out_order, std::vector<int64_t>& cnt) {
+  cnt.assign(static_cast<size_t>(n) + 1, 0);
+  for (int64_t k = 0; k < len; ++k) cnt[key[src_order ? src_order[k] : k] + 1]++;
+  for (int64_t i = 0; i < n; ++i) cnt[i + 1] += cnt[i];
+  for (int64_t k = 0; k < len; ++k) {
+    const int64_t s = src_order ? src_order[k] : k;
+    out_order[cnt[key[s]]++] = s;
+  }
+}
+
+static Schedule build_schedule_host(int64_t n, const int64_t* ptr, int max_chunk,
+                                    std::vector<Item>& items, std::vector<SplitRow>& split) {
+  Schedule s;
+  items.clear();
+  split.clear();
+  items.reserve(static_cast<size_t>(n) + 1024);
+  int64_t slots = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    const int64_t b = ptr[r], e = ptr[r + 1], deg = e - b;
+    if (deg <= max_chunk) {
+      items.push_back({static_cast<int32_t>(r), static_cast<int32_t>(b), static_cast<int32_t>(e), -1});
+    } else {
+      const int64_t nch = (deg + max_chunk - 1) / max_chunk;
+      const int64_t sz = (deg + nch - 1) / nch;
+      split.push_back({static_cast<int32_t>(r), static_cast<int32_t>(slots), static_cast<int32_t>(nch), 0});
+      for (int64_t c = 0; c < nch; ++c) {
+        const int64_t cb = b + c * sz, ce = std::min(e, cb + sz);
+        items.push_back({static_cast<int32_t>(r), static_cast<int32_t>(cb), static_cast<int32_t>(ce),
+                         static_cast<int32_t>(slots + c)});
+      }
+      slots += nch;
+    }
+  }
+  s.n_items = static_cast<int64_t>(items.size());
+  s.n_slots = slots;
+  s.n_split = static_cast<int64_t>(split.size());
+  return s;
+}
+
+template <class T>
+static int upload(T** dev, const T* host, size_t count) {
+  *dev = nullptr;
+  if (count == 0) count = 1;
+  EDIS_CUDA(cudaMalloc(reinterpret_cast<void**>(dev), count * sizeof(T)));
+  if (host) EDIS_CUDA(cudaMemcpy(*dev, host, count * sizeof(T), cudaMemcpyHostToDevice));
+  return EDIS_OK;
+}
+
+}  // namespace edis
+
+using namespace edis;
+
+extern "C" const char* edis_last_error(void) { return g_err.c_str(); }
+extern "C" const char* edis_version(void) { return "edis 0.1 sm_100a"; }
+
+// ---------------------------------------------------------------------------------------
+extern "C" int64_t edis_build_adjacency_host(int64_t n, int64_t m, const int64_t* rows,
+                                             const int64_t* cols, const double* vals,
+                                             int64_t* out_row, int64_t* out_col, float* out_val) {
+  if (n <= 0 || m < 0 || (m > 0 && (!rows || !cols)) || !out_row || !out_col || !out_val) {
+    set_error("edis_build_adjacency_host: bad arguments");
+    return EDIS_ERR_ARG;
+  }
+  // directed records: original orientation (flag 1) + mirrored (flag 2); diagonal handled apart
+  std::vector<int64_t> R, Cc;
+  std::vector<double> V;
+  std::vector<uint8_t> Fl;
+  R.reserve(2 * m);
+  Cc.reserve(2 * m);
+  V.reserve(2 * m);
+  Fl.reserve(2 * m);
+  for (int64_t k = 0; k < m; ++k) {
+    const int64_t r = rows[k], c = cols[k];
+    if (r < 0 || r >= n || c < 0 || c >= n) {
+      set_error("edis_build_adjacency_host: entry %lld = (%lld, %lld) out of range n=%lld",
+                (long long)k, (long long)r, (long long)c, (long long)n);
+      return EDIS_ERR_ARG;
+    }
+    if (r == c) continue;  // np.fill_diagonal(adj, 1) overwrites the diagonal (data_load.py:69)
+    const double v = vals ? vals[k] : 1.0;
+    R.push_back(r); Cc.push_back(c); V.push_back(v); Fl.push_back(1);
+    R.push_back(c); Cc.push_back(r); V.push_back(v); Fl.push_back(2);
+  }
+  const int64_t len = static_cast<int64_t>(R.size());
+  std::vector<int64_t> o1(len), o2(len), cnt;
+  counting_order(n, len, Cc.data(), nullptr, o1.data(), cnt);
+  counting_order(n, len, R.data(), o1.data(), o2.data(), cnt);
+  // dedup: value = max(A_ij, A_ji) with absent = 0 (data_load.py:71), then drop zeros
+  std::vector<int64_t> ur, uc;
+  std::vector<double> uv;
+  ur.reserve(len / 2 + n);
+  uc.reserve(len / 2 + n);
+  uv.reserve(len / 2 + n);
+  std::vector<double> deg(n, 0.0);
+  int64_t k = 0;
+  int64_t next_diag = 0;  // diagonal entries are merged in row-major position
+  auto emit_diag_upto = [&](int64_t row_limit, int64_t col_limit) {
+    // emit (d, d) for all pending d with (d,d) < (row_limit, col_limit) in row-major order
+    while (next_diag < n && (next_diag < row_limit || (next_diag == row_limit && next_diag < col_limit))) {
+      ur.push_back(next_diag); uc.push_back(next_diag); uv.push_back(1.0);
+      deg[next_diag] += 1.0;
+      ++next_diag;
+    }
+  };
+  while (k < len) {
+    const int64_t r = R[o2[k]], c = Cc[o2[k]];
+    double best = V[o2[k]];
+    uint8_t fl = Fl[o2[k]];
+    int64_t k2 = k + 1;
+    while (k2 < len && R[o2[k2]] == r && Cc[o2[k2]] == c) {
+      best = std::max(best, V[o2[k2]]);
+      fl |= Fl[o2[k2]];
+      ++k2;
+    }
+    if (fl != 3) best = std::max(best, 0.0);  // the other orientation is an implicit 0
+    if (best != 0.0) {
+      emit_diag_upto(r, c);
+      ur.push_back(r); uc.push_back(c); uv.push_back(best);
+      deg[r] += best;
+    }
+    k = k2;
+  }
+  emit_diag_upto(n, 0);
+  const int64_t E = static_cast<int64_t>(ur.size());
+  for (int64_t q = 0; q < E; ++q) {
+    // normalize_adj (data_load.py:12-20): r_inv = rowsum**-1 (inf -> 0), values r_inv * a (float64)
+    double rinv = std::pow(deg[ur[q]], -1.0);
+    if (std::isinf(rinv)) rinv = 0.0;
+    out_row[q] = ur[q];
+    out_col[q] = uc[q];
+    out_val[q] = static_cast<float>(rinv * uv[q]);
+  }
+  return E;
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, const int64_t* col,
+                                 int max_chunk, int device, edis_graph** out) {
+  EDIS_CHECK_ARG(out && n > 0 && e_in >= 0 && (e_in == 0 || (row && col)),
+                 "edis_graph_create: bad arguments");
+  EDIS_CHECK_ARG(e_in < (int64_t(1) << 31) - 64 && n < (int64_t(1) << 31) - 64,
+                 "edis_graph_create: n and e must fit int32");
+  if (max_chunk <= 0) max_chunk = 256;
+  bool sorted = true;
+  for (int64_t k = 0; k < e_in; ++k) {
+    if (row[k] < 0 || row[k] >= n || col[k] < 0 || col[k] >= n) {
+      set_error("edis_graph_create: entry %lld out of range", (long long)k);
+      return EDIS_ERR_ARG;
+    }
+    if (k > 0 && (row[k] < row[k - 1] || (row[k] == row[k - 1] && col[k] <= col[k - 1]))) sorted = false;
+  }
+  edis_graph* g = new edis_graph();
+  g->n = n;
+  g->e_in = e_in;
+  g->device = device;
+  g->was_sorted = sorted;
+  g->h_perm = new int64_t[std::max<int64_t>(e_in, 1)];
+  std::vector<int64_t> srow, scol;
+  if (sorted) {
+    for (int64_t k = 0; k < e_in; ++k) g->h_perm[k] = k;
+    srow.assign(row, row + e_in);
+    scol.assign(col, col + e_in);
+  } else {
+    // stable (col, then row) counting sorts + coalesce duplicates (adj.coalesce(), layers.py:344)
+    std::vector<int64_t> o1(e_in), o2(e_in), cnt;
+    counting_order(n, e_in, col, nullptr, o1.data(), cnt);
+    counting_order(n, e_in, row, o1.data(), o2.data(), cnt);
+    srow.reserve(e_in);
+    scol.reserve(e_in);
+    for (int64_t k = 0; k < e_in; ++k) {
+      const int64_t s = o2[k];
+      if (srow.empty() || srow.back() != row[s] || scol.back() != col[s]) {
+        srow.push_back(row[s]);
+        scol.push_back(col[s]);
+      }
+      g->h_perm[s] = static_cast<int64_t>(srow.size()) - 1;
+    }
+  }
+  const int64_t e = static_cast<int64_t>(srow.size());
+  g->e = e;
+  g->h_rowptr = new int64_t[n + 1]();
+  g->h_col = new int32_t[std::max<int64_t>(e, 1)];
+  g->h_cscptr = new int64_t[n + 1]();
+  g->h_cscrow = new int32_t[std::max<int64_t>(e, 1)];
+  g->h_csceid = new int32_t[std::max<int64_t>(e, 1)];
+  for (int64_t k = 0; k < e; ++k) {
+    g->h_rowptr[srow[k] + 1]++;
+    g->h_cscptr[scol[k] + 1]++;
+    g->h_col[k] = static_cast<int32_t>(scol[k]);
+  }
+  for (int64_t i = 0; i < n; ++i) {
+    g->max_in = std::max(g->max_in, g->h_rowptr[i + 1]);
+    g->max_out = std::max(g->max_out, g->h_cscptr[i + 1]);
+    g->h_rowptr[i + 1] += g->h_rowptr[i];
+    g->h_cscptr[i + 1] += g->h_cscptr[i];
+  }
+  {
+    std::vector<int64_t> cur(g->h_cscptr, g->h_cscptr + n);
+    for (int64_t k = 0; k < e; ++k) {
+      const int64_t pos = cur[scol[k]]++;
+      g->h_cscrow[pos] = static_cast<int32_t>(srow[k]);
+      g->h_csceid[pos] = static_cast<int32_t>(k);
+    }
+  }
+  std::vector<Item> items;
+  std::vector<SplitRow> split;
+  int prev_dev = 0;
+  cudaGetDevice(&prev_dev);
+  int rc = EDIS_OK;
+  auto fail = [&](int code) {
+    cudaSetDevice(prev_dev);
+    edis_graph_destroy(g);
+    return code;
+  };
+  if (cudaSetDevice(device) != cudaSuccess) {
+    set_error("edis_graph_create: cudaSetDevice(%d) failed (no CUDA device? there is no CPU fallback)", device);
+    return fail(EDIS_ERR_CUDA);
+  }
+  cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+  g->dst = build_schedule_host(n, g->h_rowptr, max_chunk, items, split);
+  if ((rc = upload(&g->dst.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->dst.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
+  g->src = build_schedule_host(n, g->h_cscptr, max_chunk, items, split);
+  if ((rc = upload(&g->src.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->src.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->rowptr, g->h_rowptr, n + 1)) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->col, g->h_col, e)) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->cscptr, g->h_cscptr, n + 1)) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->cscrow, g->h_cscrow, e)) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->csceid, g->h_csceid, e)) != EDIS_OK) return fail(rc);
+  cudaSetDevice(prev_dev);
+  *out = g;
+  return EDIS_OK;
+}
+
+extern "C" void edis_graph_destroy(edis_graph* g) {
+  if (!g) return;
+  cudaFree(g->rowptr); cudaFree(g->col); cudaFree(g->cscptr); cudaFree(g->cscrow); cudaFree(g->csceid);
+  cudaFree(g->dst.items); cudaFree(g->dst.split); cudaFree(g->src.items); cudaFree(g->src.split);
+  delete[] g->h_rowptr; delete[] g->h_col; delete[] g->h_perm;
+  delete[] g->h_cscptr; delete[] g->h_cscrow; delete[] g->h_csceid;
+  delete g;
+}
+
+extern "C" int edis_graph_info(const edis_graph* g, int64_t info[9]) {
+  EDIS_CHECK_ARG(g && info, "edis_graph_info: null argument");
+  info[0] = g->n; info[1] = g->e;
+  info[2] = g->dst.n_items; info[3] = g->dst.n_slots;
+  info[4] = g->src.n_items; info[5] = g->src.n_slots;
+  info[6] = g->max_in; info[7] = g->max_out; info[8] = g->was_sorted ? 1 : 0;
+  return EDIS_OK;
+}
+
+extern "C" int edis_graph_export(const edis_graph* g, int64_t* rowptr, int32_t* col, int64_t* perm,
+                                 int64_t* cscptr, int32_t* cscrow, int32_t* csceid) {
+  EDIS_CHECK_ARG(g, "edis_graph_export: null graph");
+  if (rowptr) memcpy(rowptr, g->h_rowptr, (g->n + 1) * sizeof(int64_t));
+  if (col) memcpy(col, g->h_col, g->e * sizeof(int32_t));
+  if (perm) memcpy(perm, g->h_perm, g->e_in * sizeof(int64_t));  // sized by the INPUT entry count
+  if (cscptr) memcpy(cscptr, g->h_cscptr, (g->n + 1) * sizeof(int64_t));
+  if (cscrow) memcpy(cscrow, g->h_cscrow, g->e * sizeof(int32_t));
+  if (csceid) memcpy(csceid, g->h_csceid, g->e * sizeof(int32_t));
+  return EDIS_OK;
+}
+
+extern "C" int64_t edis_graph_workspace_bytes(const edis_graph* g, int64_t width) {
+  if (!g || width <= 0) return EDIS_ERR_ARG;
+  const int64_t slots = std::max(g->dst.n_slots, g->src.n_slots);
+  return (slots * width + 64) * static_cast<int64_t>(sizeof(float));
+}
+
+// ---------------------------------------------------------------------------------------
+extern "C" int64_t edis_merge_pairs_host(int64_t n_hit, const int64_t* hit_key, int64_t n_forced,
+                                         const int64_t* forced_key, int64_t n_pos,
+                                         const int64_t* pos_key, int64_t* out_key, float* out_label) {
+  if (n_hit < 0 || n_forced < 0 || n_pos < 0 || !out_key || !out_label) {
+    set_error("edis_merge_pairs_host: bad arguments");
+    return EDIS_ERR_ARG;
+  }
+  std::vector<int64_t> f(forced_key, forced_key + n_forced);
+  std::sort(f.begin(), f.end());
+  const bool hit_sorted = std::is_sorted(hit_key, hit_key + n_hit);
+  std::vector<int64_t> hs;
+  const int64_t* h = hit_key;
+  if (!hit_sorted) {
+    hs.assign(hit_key, hit_key + n_hit);
+    std::sort(hs.begin(), hs.end());
+    h = hs.data();
+  }
+  // merge + dedup (mask.nonzero() is row-major sorted and unique, pretrainer.py:703)
+  int64_t a = 0, b = 0, m = 0, p = 0;
+  while (a < n_hit || b < n_forced) {
+    int64_t key;
+    if (b >= n_forced || (a < n_hit && h[a] <= f[b])) key = h[a++]; else key = f[b++];
+    if (m > 0 && out_key[m - 1] == key) continue;
+    while (p < n_pos && pos_key[p] < key) ++p;
+    out_label[m] = (p < n_pos && pos_key[p] == key) ? 1.0f : 0.0f;  // label[indices] (704)
+    out_key[m++] = key;
+  }
+  return m;
+}

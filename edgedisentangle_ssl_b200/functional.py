@@ -1,0 +1,384 @@
+"""torch.autograd.Function wrappers over the C ABI (include/edis.h).
+
+PyTorch is plumbing here: it owns device memory, streams and the dense GEMMs; every sparse /
+segment / reduction step runs in libedis.so on the caller's current CUDA stream.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+from ._lib import LayerDesc, check, lib
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _off(t, col):
+    """Device pointer of column `col` of a 2-D fp32 tensor."""
+    return ctypes.c_void_p(t.data_ptr() + 4 * int(col))
+
+
+def _rows(t, what):
+    """(tensor, leading stride) of a 2-D fp32 CUDA tensor with unit inner stride."""
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise _lib.EdisError("%s must be a float32 CUDA tensor (got %s on %s)" % (what, t.dtype, t.device))
+    if t.dim() != 2 or t.stride(1) != 1:
+        t = t.contiguous()
+    return t, t.stride(0)
+
+
+class KernelTimer:
+    """Optional per-call CUDA-event timing + launch counting (bench.py switches it on).
+
+    Events are recorded on the stream the kernels are launched on; durations are read after
+    the caller synchronises.  Off by default: zero overhead on the product path."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = {}     # name -> list of (start_event, end_event)
+        self.launches = 0
+
+    def reset(self):
+        self.records = {}
+        self.launches = 0
+
+    def durations_ms(self):
+        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.records.items()}
+
+
+TIMER = KernelTimer()
+
+
+class _timed:
+    def __init__(self, name, graph, launches):
+        self.name, self.launches = name, launches
+
+    def __enter__(self):
+        if TIMER.enabled:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.end = torch.cuda.Event(enable_timing=True)
+            self.start.record(torch.cuda.current_stream())
+        return self
+
+    def __exit__(self, *exc):
+        if TIMER.enabled:
+            self.end.record(torch.cuda.current_stream())
+            TIMER.records.setdefault(self.name, []).append((self.start, self.end))
+            TIMER.launches += self.launches
+        return False
+
+
+def _desc(att, C, D, training=False, p=0.0, seed=0):
+    return LayerDesc(att=att, C=C, D=D, Dv=D, training=1 if (training and p > 0) else 0, p=float(p),
+                     seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
+
+
+def _workspace(graph, width, like):
+    nbytes = graph.workspace_bytes(width)
+    return torch.empty(nbytes, dtype=torch.uint8, device=like.device), nbytes
+
+
+class DisGAFused(torch.autograd.Function):
+    """All C channels of one DisGALayer: scoring -> sigmoid -> segment softmax -> dropout ->
+    aggregation -> (+bias) -> ELU.  Replaces layers.py:349-416 + 500/509 per channel.
+
+    forward(graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias, training, p, seed)
+        -> (out[N, C*D], edge_e[E, C])
+    `proj` is the output of the layer's single projection GEMM, [N, W]; the operands are column
+    blocks of it (no copies): V = proj[:, off_v:off_v+C*D] and, for att 2/3,
+    P = proj[:, off_p:...], Q = proj[:, off_q:...] (att 2: off_p == off_q).  For att 1 the
+    per-node scalars sdst/ssrc [N, C] are passed instead.  The backward writes gP/gQ/gV
+    straight into one [N, W] gradient buffer for the GEMM's backward.
+    """
+
+    @staticmethod
+    def forward(ctx, graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias, training, p, seed):
+        proj, ld = _rows(proj, "proj")
+        CD = C * D
+        if att == 1:
+            sdst, ssrc = sdst.contiguous(), ssrc.contiguous()
+            P, Q, ldp, ldq = _ptr(sdst), _ptr(ssrc), C, C
+        else:
+            P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
+        a = a.contiguous() if a is not None else None
+        bias = bias.contiguous() if bias is not None else None
+        n, e = graph.n, graph.e
+        out = torch.empty(n, CD, dtype=torch.float32, device=proj.device)
+        hpre = torch.empty_like(out)
+        edge_e = torch.empty(e, C, dtype=torch.float32, device=proj.device)
+        stats = torch.empty(n, 2 * C, dtype=torch.float32, device=proj.device)
+        ws, nbytes = _workspace(graph, CD + 2 * C, proj)
+        d = _desc(att, C, D, training, p, seed)
+        with _timed("disga_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
+            check(lib.edis_disga_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a),
+                                     _off(proj, off_v), ld, _ptr(bias), _ptr(out), _ptr(hpre), _ptr(edge_e),
+                                     _ptr(stats), _ptr(ws), nbytes, _stream()), "edis_disga_fwd")
+        ctx.graph, ctx.d, ctx.offs = graph, d, (off_p, off_q, off_v)
+        ctx.has_a, ctx.has_bias = a is not None, bias is not None
+        ctx.save_for_backward(proj, sdst, ssrc, a, bias, hpre, edge_e, stats)
+        ctx.set_materialize_grads(False)
+        return out, edge_e
+
+    @staticmethod
+    def backward(ctx, g_out, g_edge_e):
+        proj, sdst, ssrc, a, bias, hpre, edge_e, stats = ctx.saved_tensors
+        graph, d = ctx.graph, ctx.d
+        C, D, att = d.C, d.D, d.att
+        CD = C * D
+        n, e = graph.n, graph.e
+        off_p, off_q, off_v = ctx.offs
+        ld, W, dev = proj.stride(0), proj.shape[1], proj.device
+        if g_out is None:
+            g_out = torch.zeros(n, CD, dtype=torch.float32, device=dev)
+        g_out = g_out.contiguous()
+        if g_edge_e is not None:
+            g_edge_e = g_edge_e.contiguous()
+        g_sd = g_ss = gq_sep = None
+        if att == 1:
+            # the score columns of proj get their gradient through sdst/ssrc in torch
+            g_proj = torch.zeros(n, W, dtype=torch.float32, device=dev)
+            g_sd = torch.empty(n, C, dtype=torch.float32, device=dev)
+            g_ss = torch.empty(n, C, dtype=torch.float32, device=dev)
+            P, Q, ldp, ldq = _ptr(sdst), _ptr(ssrc), C, C
+            gP, gQ, ldgp, ldgq = _ptr(g_sd), _ptr(g_ss), C, C
+        else:
+            covered = CD * (3 if att == 3 else 2)
+            g_proj = (torch.empty if W == covered else torch.zeros)(n, W, dtype=torch.float32, device=dev)
+            P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
+            gP, ldgp = _off(g_proj, off_p), W
+            if off_q == off_p:      # att 2: P and Q are the same columns; sum the two grads
+                gq_sep = torch.empty(n, CD, dtype=torch.float32, device=dev)
+                gQ, ldgq = _ptr(gq_sep), CD
+            else:
+                gQ, ldgq = _off(g_proj, off_q), W
+        ga = torch.zeros(C, D, dtype=torch.float32, device=dev) if att == 3 else None
+        edge_rec = torch.empty(e, 2 * C, dtype=torch.float32, device=dev)
+        gh = torch.empty(n, CD, dtype=torch.float32, device=dev)
+        ws, nbytes = _workspace(graph, 2 * CD + 2 * C, proj)
+        args = (graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _off(proj, off_v), ld, _ptr(bias),
+                _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(g_out), _ptr(g_edge_e), gP, ldgp, gQ, ldgq,
+                _ptr(ga), _off(g_proj, off_v), W, _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream())
+        with _timed("disga_bwd_dst", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
+            check(lib.edis_disga_bwd_dst(*args), "edis_disga_bwd_dst")
+        with _timed("disga_bwd_src", graph, 1 + (2 if graph.info["src_slots"] else 0)):
+            check(lib.edis_disga_bwd_src(*args), "edis_disga_bwd_src")
+        if gq_sep is not None:
+            g_proj[:, off_p:off_p + CD] += gq_sep
+        gbias = gh.sum(0) if ctx.has_bias else None
+        return (None, None, None, None, g_proj, None, None, None, g_sd, g_ss,
+                ga if ctx.has_a else None, gbias, None, None, None)
+
+
+class SageFused(torch.autograd.Function):
+    """gnn_type=SAGE: scoring -> softmax -> dropout -> neighbour mean of the RAW input x shared
+    by all channels, divided by the detached (row sum + 1).  Replaces layers.py:349-394 +
+    400-403 + SageConv.forward's aggregation (layers.py:96-103, incl. its N x N `to_dense()`).
+
+    forward(graph, att, C, D, P, Q, a, X, training, p, seed) -> (neigh[N, C*F], edge_e[E, C])
+    """
+
+    @staticmethod
+    def forward(ctx, graph, att, C, D, P, Q, a, X, training, p, seed):
+        P, ldp = _rows(P, "P")
+        Q, ldq = _rows(Q, "Q")
+        X, ldx = _rows(X, "X")
+        a = a.contiguous() if a is not None else None
+        n, e, Fin = graph.n, graph.e, X.shape[1]
+        neigh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
+        edge_e = torch.empty(e, C, dtype=torch.float32, device=X.device)
+        stats = torch.empty(n, 2 * C, dtype=torch.float32, device=X.device)
+        ws, nbytes = _workspace(graph, C * Fin + 2 * C, X)
+        d = _desc(att, C, D, training, p, seed)
+        d.Dv = Fin
+        check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), _ptr(P), ldp, _ptr(Q), ldq, _ptr(a),
+                                      _ptr(X), ldx, _ptr(neigh), _ptr(edge_e), _ptr(stats), _ptr(ws), nbytes,
+                                      _stream()), "edis_disga_sage_fwd")
+        ctx.graph, ctx.d, ctx.lds = graph, d, (ldp, ldq, ldx)
+        ctx.has_a = a is not None
+        ctx.save_for_backward(P, Q, a, X, neigh, edge_e, stats)
+        ctx.set_materialize_grads(False)
+        return neigh, edge_e
+
+    @staticmethod
+    def backward(ctx, g_neigh, g_edge_e):
+        P, Q, a, X, neigh, edge_e, stats = ctx.saved_tensors
+        graph, d = ctx.graph, ctx.d
+        C, D, att, Fin = d.C, d.D, d.att, d.Dv
+        n, e = graph.n, graph.e
+        ldp, ldq, ldx = ctx.lds
+        if g_neigh is None:
+            g_neigh = torch.zeros_like(neigh)
+        g_neigh = g_neigh.contiguous()
+        if g_edge_e is not None:
+            g_edge_e = g_edge_e.contiguous()
+        wdt = C if att == 1 else C * D
+        gP = torch.empty(n, wdt, dtype=torch.float32, device=X.device)
+        gQ = torch.empty(n, wdt, dtype=torch.float32, device=X.device)
+        gX = torch.empty(n, Fin, dtype=torch.float32, device=X.device)
+        ga = torch.zeros(C, D, dtype=torch.float32, device=X.device) if att == 3 else None
+        edge_rec = torch.empty(e, 2 * C, dtype=torch.float32, device=X.device)
+        gh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
+        ws, nbytes = _workspace(graph, 2 * C * D + 2 * C + Fin, X)
+        check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), _ptr(P), ldp, _ptr(Q), ldq, _ptr(a),
+                                      _ptr(X), ldx, _ptr(neigh), _ptr(edge_e), _ptr(stats), _ptr(g_neigh),
+                                      _ptr(g_edge_e), _ptr(gP), _ptr(gQ), _ptr(ga), _ptr(gX), _ptr(edge_rec),
+                                      _ptr(gh), _ptr(ws), nbytes, _stream()), "edis_disga_sage_bwd")
+        return (None, None, None, None, gP, gQ, ga if ctx.has_a else None, gX, None, None, None)
+
+
+class PairScore(torch.autograd.Function):
+    """Raw attention logits of channels [c_lo, c_hi) on an arbitrary (i, j) pair list.
+    Replaces layers.py:355-360 / 368-372 / 381-389.  Returns [M, c_hi - c_lo]."""
+
+    @staticmethod
+    def forward(ctx, att, C, D, pi, pj, c_lo, c_hi, P, Q, a):
+        P, ldp = _rows(P, "P")
+        Q, ldq = _rows(Q, "Q")
+        a = a.contiguous() if a is not None else None
+        pi = pi.contiguous()
+        pj = pj.contiguous()
+        if pi.dtype != torch.int64 or pj.dtype != torch.int64 or not pi.is_cuda:
+            raise _lib.EdisError("pair indices must be int64 CUDA tensors")
+        m, n = pi.numel(), P.shape[0]
+        out = torch.empty(m, c_hi - c_lo, dtype=torch.float32, device=P.device)
+        d = _desc(att, C, D)
+        check(lib.edis_pair_score_fwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
+                                      _ptr(Q), ldq, _ptr(a), _ptr(out), _stream()), "edis_pair_score_fwd")
+        ctx.d, ctx.rng, ctx.lds = d, (c_lo, c_hi), (ldp, ldq)
+        ctx.has_a = a is not None
+        ctx.save_for_backward(pi, pj, P, Q, a)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        pi, pj, P, Q, a = ctx.saved_tensors
+        d = ctx.d
+        c_lo, c_hi = ctx.rng
+        ldp, ldq = ctx.lds
+        n, m = P.shape[0], pi.numel()
+        wdt = d.C if d.att == 1 else d.C * d.D
+        gP = torch.zeros(n, wdt, dtype=torch.float32, device=P.device)
+        gQ = torch.zeros(n, wdt, dtype=torch.float32, device=P.device)
+        ga = torch.zeros(d.C, d.D, dtype=torch.float32, device=P.device) if d.att == 3 else None
+        g_out = g_out.contiguous()
+        check(lib.edis_pair_score_bwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
+                                      _ptr(Q), ldq, _ptr(a), _ptr(g_out), _ptr(gP), _ptr(gQ), _ptr(ga),
+                                      _stream()), "edis_pair_score_bwd")
+        return (None, None, None, None, None, None, None, gP, gQ, ga if ctx.has_a else None)
+
+
+class SslWmse(torch.autograd.Function):
+    """mean_k w_k (sigmoid(sum_c scores[k, c]) - target_k)^2 with the reference's class
+    weights.  Replaces pretrainer.py:730-737 / 613-627 + utils.adj_mse_loss (utils.py:287-298)."""
+
+    @staticmethod
+    def forward(ctx, scores, target, n_pos):
+        scores = scores.contiguous()
+        target = target.contiguous()
+        m, cs = scores.shape
+        loss = torch.empty(1, dtype=torch.float32, device=scores.device)
+        ws = torch.empty(8, dtype=torch.uint8, device=scores.device)
+        check(lib.edis_ssl_wmse_fwd(m, cs, _ptr(scores), _ptr(target), int(n_pos), _ptr(loss), _ptr(ws), 8,
+                                    _stream()), "edis_ssl_wmse_fwd")
+        ctx.n_pos = int(n_pos)
+        ctx.save_for_backward(scores, target)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        scores, target = ctx.saved_tensors
+        m, cs = scores.shape
+        g_scores = torch.empty_like(scores)
+        g_loss = g_loss.reshape(1).contiguous().float()
+        check(lib.edis_ssl_wmse_bwd(m, cs, _ptr(scores), _ptr(target), ctx.n_pos, _ptr(g_loss),
+                                    _ptr(g_scores), _stream()), "edis_ssl_wmse_bwd")
+        return g_scores, None, None
+
+
+class NllConstLabel(torch.autograd.Function):
+    """mean_i -log_softmax(logits[i])[label], one label for all rows (DifHead tail,
+    pretrainer.py:825-832 + models.py:540-541)."""
+
+    @staticmethod
+    def forward(ctx, logits, label):
+        logits = logits.contiguous()
+        n, k = logits.shape
+        loss = torch.empty(1, dtype=torch.float32, device=logits.device)
+        ws = torch.empty(8, dtype=torch.uint8, device=logits.device)
+        check(lib.edis_nll_const_label_fwd(n, k, _ptr(logits), int(label), _ptr(loss), _ptr(ws), 8, _stream()),
+              "edis_nll_const_label_fwd")
+        ctx.label = int(label)
+        ctx.save_for_backward(logits)
+        return loss.reshape(())
+
+    @staticmethod
+    def backward(ctx, g_loss):
+        (logits,) = ctx.saved_tensors
+        n, k = logits.shape
+        g_logits = torch.empty_like(logits)
+        g_loss = g_loss.reshape(1).contiguous().float()
+        check(lib.edis_nll_const_label_bwd(n, k, _ptr(logits), ctx.label, _ptr(g_loss), _ptr(g_logits),
+                                           _stream()), "edis_nll_const_label_bwd")
+        return g_logits, None
+
+
+class SpSoftmax(torch.autograd.Function):
+    """utils.sp_softmax (utils.py:192-200) on a COO row index list."""
+
+    @staticmethod
+    def forward(ctx, row, values, n):
+        shape = values.shape
+        v = values.reshape(-1).contiguous()
+        row = row.contiguous()
+        out = torch.empty_like(v)
+        denom = torch.empty(n, dtype=torch.float32, device=v.device)
+        vmax = torch.empty(1, dtype=torch.float32, device=v.device)
+        check(lib.edis_sp_softmax_fwd(n, v.numel(), _ptr(row), _ptr(v), _ptr(out), _ptr(denom), _ptr(vmax),
+                                      _stream()), "edis_sp_softmax_fwd")
+        ctx.n, ctx.shape = n, shape
+        ctx.save_for_backward(row, out)
+        return out.reshape(shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        row, out = ctx.saved_tensors
+        g = g.reshape(-1).contiguous()
+        gv = torch.empty_like(out)
+        rowdot = torch.empty(ctx.n, dtype=torch.float32, device=out.device)
+        check(lib.edis_sp_softmax_bwd(ctx.n, out.numel(), _ptr(row), _ptr(out), _ptr(g), _ptr(gv), _ptr(rowdot),
+                                      _stream()), "edis_sp_softmax_bwd")
+        return None, gv.reshape(ctx.shape), None
+
+
+class SpMatmul(torch.autograd.Function):
+    """utils.sp_matmul (utils.py:203-207) on COO (row, col) index lists."""
+
+    @staticmethod
+    def forward(ctx, row, col, values, mat):
+        v = values.reshape(-1).contiguous()
+        mat = mat.contiguous()
+        row, col = row.contiguous(), col.contiguous()
+        n, f = mat.shape
+        out = torch.empty_like(mat)
+        check(lib.edis_sp_matmul_fwd(n, v.numel(), f, _ptr(row), _ptr(col), _ptr(v), _ptr(mat), _ptr(out),
+                                     _stream()), "edis_sp_matmul_fwd")
+        ctx.vshape = values.shape
+        ctx.save_for_backward(row, col, v, mat)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        row, col, v, mat = ctx.saved_tensors
+        n, f = mat.shape
+        g = g.contiguous()
+        gv = torch.empty_like(v)
+        gm = torch.empty_like(mat)
+        check(lib.edis_sp_matmul_bwd(n, v.numel(), f, _ptr(row), _ptr(col), _ptr(v), _ptr(mat), _ptr(g),
+                                     _ptr(gv), _ptr(gm), _stream()), "edis_sp_matmul_bwd")
+        return None, None, gv.reshape(ctx.vshape), gm

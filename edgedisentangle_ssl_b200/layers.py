@@ -1,0 +1,217 @@
+"""Drop-in DISGAT layers on the B200 path (mirrors /root/reference/layers.py for this path).
+
+Same class names, constructor signatures, parameter names / shapes / init order as the
+reference, so a reference `state_dict` loads unchanged and same-seed initialisation is equal:
+  DisGALayer      layers.py:303-511   (sparse branch only; the dense branch is out of scope)
+  FuseLayer       layers.py:876-921
+  SageConv        layers.py:63-112    (parameters + projection; aggregation is fused upstream)
+  GraphConvolution layers.py:16-59    (parameters; aggregation is fused upstream)
+All channels of a DISGAT layer run in ONE fused kernel launch (`run_channels`).
+"""
+import itertools
+import math
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+from torch.nn.parameter import Parameter
+
+from . import _lib
+from .functional import DisGAFused, PairScore, SageFused
+from .graph import as_graph
+
+_seed_counter = itertools.count(1)
+
+
+def _next_seed():
+    # counter-based dropout stream derived from torch's seed: no device->host sync
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+
+
+class GraphConvolution(nn.Module):
+    """Parameters of the reference GCN layer (layers.py:16-59): weight[F, D], bias[D]."""
+
+    def __init__(self, in_features, out_features, bias=True):
+        super().__init__()
+        self.in_features, self.out_features = in_features, out_features
+        self.weight = Parameter(torch.FloatTensor(in_features, out_features))
+        if bias:
+            self.bias = Parameter(torch.FloatTensor(out_features))
+        else:
+            self.register_parameter("bias", None)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        stdv = 1.0 / math.sqrt(self.weight.size(1))
+        self.weight.data.uniform_(-stdv, stdv)
+        if self.bias is not None:
+            self.bias.data.uniform_(-stdv, stdv)
+
+
+class SageConv(nn.Module):
+    """Parameters of the reference GraphSage layer (layers.py:63-112): proj = Linear(2F, D)."""
+
+    def __init__(self, in_features, out_features, bias=False):
+        super().__init__()
+        self.proj = nn.Linear(in_features * 2, out_features, bias=bias)
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        nn.init.normal_(self.proj.weight)
+        if self.proj.bias is not None:
+            nn.init.constant_(self.proj.bias, 0.0)
+
+
+def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
+    """Run C DisGALayer channels that share an input as one fused launch.
+
+    chs: list of DisGALayer with identical (in, out, att, gnn).  Returns
+      out    [N, C*D] = cat_c elu(h'_c)  (None if aggregate=False)
+      edge_e [E, C]   raw logits           (None if aggregate=False)
+      auxs   list over pair sets of [M_k, c_hi-c_lo] logits (None if aux is None)
+    The dense projections are ordinary fp32 torch GEMMs (one per layer, all channels and all
+    operands concatenated); everything per-edge happens in libedis.so.
+    """
+    l0 = chs[0]
+    C, D, Fin, att, gnn = len(chs), l0.out_features, l0.in_features, l0.att_type, l0.gnn_type
+    if x.dtype != torch.float32 or not x.is_cuda:
+        raise _lib.EdisError("DisGALayer input must be a float32 CUDA tensor; there is no CPU fallback")
+    CD = C * D
+    a = None
+    if att == 3:
+        a = torch.cat([l.a.reshape(1, D) for l in chs], 0)
+        w_score = [torch.cat([l.W[:Fin] for l in chs], 1), torch.cat([l.W[Fin:] for l in chs], 1)]
+    else:
+        w_score = [torch.cat([l.W for l in chs], 1)]
+    bias = None
+    w_val = []
+    if aggregate and gnn == "AT":
+        w_val = [torch.cat([l.W_em for l in chs], 1)]
+    elif aggregate and gnn == "GCN":
+        w_val = [torch.cat([l.ag_layer.weight for l in chs], 1)]
+        if l0.ag_layer.bias is not None:
+            bias = torch.cat([l.ag_layer.bias for l in chs], 0)
+    proj = x @ torch.cat(w_score + w_val, 1)          # [N, (1|2 + 0|1) * C*D], fp32 (TF32 off)
+    sdst = ssrc = None
+    if att == 3:
+        off_p, off_q, off_v = 0, CD, 2 * CD
+        P, Q = proj[:, :CD], proj[:, CD:2 * CD]
+    else:
+        off_p, off_q, off_v = 0, 0, CD
+        P = Q = proj[:, :CD]
+        if att == 1:
+            h3 = P.reshape(-1, C, D)
+            a_top = torch.cat([l.a[:D].reshape(1, D) for l in chs], 0)
+            a_bot = torch.cat([l.a[D:].reshape(1, D) for l in chs], 0)
+            P = sdst = (h3 * a_top).sum(-1)           # [N, C] destination-side scalar
+            Q = ssrc = (h3 * a_bot).sum(-1)           # [N, C] source-side scalar
+    auxs = None
+    if aux is not None:
+        auxs = []
+        for k, pairs in enumerate(aux):
+            lo, hi = (0, C) if aux_ranges is None else aux_ranges[k]
+            auxs.append(PairScore.apply(att, C, D, pairs[0], pairs[1], lo, hi, P, Q, a))
+    if not aggregate:
+        return None, None, auxs
+    training, p = l0.training, l0.dropout
+    seed = _next_seed() if (training and p > 0) else 0
+    if gnn == "SAGE":
+        neigh, edge_e = SageFused.apply(graph, att, C, D, P, Q, a, x, training, p, seed)   # [N, C*F]
+        wp = torch.stack([l.ag_layer.proj.weight for l in chs], 0)                         # [C, D, 2F]
+        self_part = torch.einsum("nf,cdf->ncd", x, wp[:, :, :Fin])
+        neigh_part = torch.einsum("ncf,cdf->ncd", neigh.reshape(-1, C, Fin), wp[:, :, Fin:])
+        h = self_part + neigh_part
+        if l0.ag_layer.proj.bias is not None:
+            h = h + torch.stack([l.ag_layer.proj.bias for l in chs], 0)
+        out = F.elu(h).reshape(-1, CD)
+    else:
+        out, edge_e = DisGAFused.apply(graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias,
+                                       training, p, seed)
+    return out, edge_e, auxs
+
+
+class DisGALayer(nn.Module):
+    """One disentangled attention channel; drop-in for layers.py:303-511 (sparse branch)."""
+
+    def __init__(self, in_features, out_features, dropout, alpha, concat=True, att_type=1, gnn_type="AT"):
+        super().__init__()
+        self.dropout = dropout
+        self.in_features = in_features
+        self.out_features = out_features
+        self.alpha = alpha          # stored but unused, like the reference (leaky slope is 0.01)
+        self.concat = concat
+        self.att_type = att_type
+        self.gnn_type = gnn_type
+        if att_type == 3:
+            self.W = nn.Parameter(torch.zeros(size=(in_features * 2, out_features)))
+            nn.init.xavier_uniform_(self.W.data, gain=1.414)
+            self.a = nn.Parameter(torch.zeros(size=(out_features, 1)))
+            nn.init.xavier_uniform_(self.a.data, gain=1.414)
+        else:
+            self.W = nn.Parameter(torch.zeros(size=(in_features, out_features)))
+            nn.init.xavier_uniform_(self.W.data, gain=1.414)
+            self.a = nn.Parameter(torch.zeros(size=(2 * out_features, 1)))
+            nn.init.xavier_uniform_(self.a.data, gain=1.414)
+        if gnn_type == "AT":
+            self.W_em = nn.Parameter(torch.zeros(size=(in_features, out_features)))
+            nn.init.xavier_uniform_(self.W_em.data, gain=1.414)
+        elif gnn_type == "SAGE":
+            self.ag_layer = SageConv(in_features, out_features)
+        elif gnn_type == "GCN":
+            self.ag_layer = GraphConvolution(in_features, out_features)
+        else:
+            raise ValueError("not implemented for gnn_type {} in DISGAT".format(gnn_type))
+
+    def forward(self, input, adj, aux_indices=None):
+        """-> (elu(h')[N, D], edge_e[E, 1]) or (..., [aux_k[M_k, 1]]) like layers.py:493-511."""
+        graph = as_graph(adj)
+        if aux_indices is not None and not isinstance(aux_indices, (list, tuple)):
+            aux_indices = [aux_indices]
+        out, edge_e, auxs = run_channels([self], input, graph, aux_indices)
+        if not self.concat:
+            raise _lib.EdisError("concat=False is not used by DISGAT (models.py:163,168) and not built")
+        if aux_indices is not None:
+            return out, edge_e, auxs
+        return out, edge_e
+
+
+class FuseLayer(nn.Module):
+    """Fuses the C channel outputs; drop-in for layers.py:876-921.
+
+    `forward` also accepts the channel-fused [N, C*D] tensor directly, which makes the
+    reference's `torch.cat(feature_list, -1)` (layers.py:900) free.
+    """
+
+    def __init__(self, args, nheads, nfeat=64, residue=0):
+        super().__init__()
+        self.args = args
+        self.nheads = nheads
+        self.nfeat = nfeat
+        self.residue_dim = residue
+        if self.args.residue_type == 0:
+            self.fuse = nn.Linear(self.nfeat * nheads + self.residue_dim, self.nfeat)
+        if self.args.residue_type == 1:
+            self.fuse = nn.Linear(self.nfeat * nheads + self.residue_dim, self.nfeat * 2)
+            self.fuse2 = nn.Linear(self.nfeat * 2, self.nfeat)
+        if self.args.residue_type == 2:
+            self.fuse = nn.Linear(self.nfeat * nheads, self.nfeat)
+            if self.residue_dim != 0:
+                self.fuse2 = nn.Linear(self.residue_dim, self.nfeat)
+
+    def forward(self, feature_list, residue=None):
+        features = feature_list if torch.is_tensor(feature_list) else torch.cat(feature_list, dim=-1)
+        use_res = self.residue_dim != 0 and residue is not None
+        rt = self.args.residue_type
+        if rt == 0:
+            if use_res:
+                features = torch.cat([features, residue], dim=-1)
+            feature = self.fuse(features)
+        elif rt == 1:
+            if use_res:
+                features = torch.cat([features, residue], dim=-1)
+            feature = self.fuse2(F.leaky_relu(self.fuse(features)))
+        elif rt == 2:
+            feature = self.fuse(features)
+            if use_res:
+                feature = feature + self.fuse2(residue)
+        return feature if self.args.fuse_no_relu else F.leaky_relu(feature)

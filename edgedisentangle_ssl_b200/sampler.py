@@ -1,0 +1,63 @@
+"""Streaming, bit-exact SSL pair sampler (host side).
+
+Replaces `SupEdgeTrainer.sample_train` (pretrainer.py:683-707) and the per-label-set body of
+`GeneratedEdgeTrainer.sample_train` (pretrainer.py:552-574) without any N x N tensor: the
+Bernoulli mask is replayed from the SAME torch CPU generator in row chunks (torch.rand fills
+serially, so chunked draws consume the stream exactly like one `torch.rand(N, N)`), the
+positives come from the CSR edge list, and the merge / dedup / labelling is integer work in
+libedis.so (`edis_merge_pairs_host`).  Memory O(chunk_rows * N); RNG work stays O(N^2), which
+is what bit-exactness with the reference's definition costs.
+"""
+from ctypes import c_float, c_int64
+
+import numpy as np
+import torch
+
+from ._lib import check, lib, np_ptr
+
+
+def homo_hetero_split(indices, labels):
+    """DisEdge label sets as edge lists (replaces the dense masks of pretrainer.py:440-456)."""
+    indices = np.asarray(indices)
+    labels = np.asarray(labels)
+    same = labels[indices[0]] == labels[indices[1]]
+    return np.ascontiguousarray(indices[:, same]), np.ascontiguousarray(indices[:, ~same])
+
+
+def sample_pairs(n, pos_indices, chunk_rows=None):
+    """One `sample_train` draw for one label set.
+
+    pos_indices: [2, E_L] int64, row-major sorted positive entries (the label matrix's nonzeros).
+    Consumes torch's CPU default generator (N*N uniforms) and numpy's global RNG (one shuffle),
+    in the reference's order.  Returns (indices[2, M] int64 row-major sorted, label[M] float32).
+    """
+    pos_indices = np.ascontiguousarray(pos_indices, dtype=np.int64)
+    e_l = pos_indices.shape[1]
+    # pretrainer.py:690-692: float32 tensor division, then python-double * 3
+    thr = (torch.tensor(float(e_l), dtype=torch.float32) / (n * n)).item() * 3
+    if chunk_rows is None:
+        chunk_rows = max(1, min(n, (1 << 24) // max(n, 1)))
+    hits = []
+    for r0 in range(0, n, chunk_rows):
+        r1 = min(n, r0 + chunk_rows)
+        nz = (torch.rand(size=(r1 - r0, n)) < thr).nonzero()
+        if nz.numel():
+            nz = nz.numpy()
+            hits.append((nz[:, 0].astype(np.int64) + r0) * n + nz[:, 1])
+    hit = np.concatenate(hits) if hits else np.empty(0, dtype=np.int64)
+    pos = np.ascontiguousarray(pos_indices.T)          # [E_L, 2] == adj.nonzero() order (697)
+    np.random.shuffle(pos)                             # row shuffle (699)
+    forced = pos[: e_l // 3]
+    forced_key = np.ascontiguousarray(forced[:, 0] * n + forced[:, 1])
+    pos_key = np.ascontiguousarray(pos_indices[0] * n + pos_indices[1])
+    if e_l > 1 and not np.all(pos_key[1:] > pos_key[:-1]):
+        pos_key = np.unique(pos_key)
+    cap = hit.shape[0] + forced_key.shape[0]
+    out_key = np.empty(max(cap, 1), dtype=np.int64)
+    out_lab = np.empty(max(cap, 1), dtype=np.float32)
+    m = lib.edis_merge_pairs_host(hit.shape[0], np_ptr(hit, c_int64), forced_key.shape[0],
+                                  np_ptr(forced_key, c_int64), pos_key.shape[0], np_ptr(pos_key, c_int64),
+                                  np_ptr(out_key, c_int64), np_ptr(out_lab, c_float))
+    check(m, "edis_merge_pairs_host")
+    key = out_key[:m]
+    return np.stack([key // n, key % n]), out_lab[:m].copy()

@@ -1,0 +1,407 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).
+
+Everything here goes through the C ABI (ctypes -> libedis.so) and is compared with
+  (i) golden vectors produced by the unmodified reference (tests/golden/*.npz), and
+  (ii) the CPU oracle (oracle/) on seeded random graphs with hubs, split rows, ragged shapes.
+Tolerance: 1e-5 relative to the tensor's scale for fp32 results (north_star); bit-exact for
+graph structure.
+"""
+import numpy as np
+import pytest
+import torch
+
+import edgedisentangle_ssl_b200 as edis
+from edgedisentangle_ssl_b200 import functional as Fn
+from edgedisentangle_ssl_b200.layers import run_channels
+from oracle import disgat as od
+from oracle import graph as og
+from helpers import load, t, assert_close, params_from, rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+RT = 1e-5
+RT_GRAD = 2e-5   # parameter gradients: long reassociated sums over edges / nodes
+
+
+def cuda_adj(n, indices):
+    idx = torch.as_tensor(indices, dtype=torch.int64)
+    return torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).to(DEV)
+
+
+def hub_graph(n, m, seed, hub_deg=None):
+    rng = np.random.RandomState(seed)
+    src = rng.randint(0, n, size=m)
+    dst = rng.randint(0, n, size=m)
+    hub_deg = hub_deg or n // 2
+    dst[:hub_deg] = 1                      # a hub destination (long CSR row)
+    src[:hub_deg] = rng.permutation(n)[:hub_deg]
+    idx, _ = og.build_adjacency(n, dst, src)
+    return idx
+
+
+# ------------------------------------------------------------------ graph handle
+def test_graph_handle_csr_csc():
+    g = load("layer_s64")
+    n, idx = int(g["n"]), g["indices"]
+    gr = edis.Graph(n, idx[0], idx[1], device=DEV, max_chunk=8)
+    ex = gr.export()
+    assert gr.e == idx.shape[1] and gr.info["was_sorted"]
+    assert np.array_equal(ex["rowptr"], np.concatenate([[0], np.cumsum(np.bincount(idx[0], minlength=n))]))
+    assert np.array_equal(ex["col"], idx[1].astype(np.int32))
+    assert np.array_equal(ex["perm"], np.arange(gr.e))
+    assert np.array_equal(gr.indices.cpu().numpy(), idx)
+    # CSC: slot k of column j holds (row, csr slot) sorted by row
+    eid = ex["csceid"]
+    assert np.array_equal(np.sort(eid), np.arange(gr.e))
+    assert np.array_equal(idx[0][eid], ex["cscrow"])
+    assert np.array_equal(np.repeat(np.arange(n), np.diff(ex["cscptr"])), idx[1][eid])
+    assert gr.info["dst_slots"] > 0 and gr.info["max_in"] > 8   # hub row got split
+
+
+def test_graph_handle_unsorted_duplicates():
+    rng = np.random.RandomState(0)
+    n = 50
+    r, c = rng.randint(0, n, 400), rng.randint(0, n, 400)
+    gr = edis.Graph(n, r, c, device=DEV)
+    key = np.unique(r * n + c)
+    ex = gr.export()
+    assert gr.e == key.shape[0] and not gr.info["was_sorted"]
+    rows = np.repeat(np.arange(n), np.diff(ex["rowptr"]))
+    assert np.array_equal(rows * n + ex["col"], key)
+    assert np.array_equal(key[ex["perm"]], r * n + c)   # every input entry maps to its slot
+
+
+# ------------------------------------------------------------------ one channel vs reference golden
+def make_layer(g, k, fin, dd, att, gnn):
+    lay = edis.DisGALayer(fin, dd, dropout=0.3, alpha=0.1, concat=True, att_type=att, gnn_type=gnn)
+    sd = {name: v for name, v in params_from(g, k + "p.").items()}
+    lay.load_state_dict(sd, strict=True)
+    return lay.to(DEV).eval()
+
+
+@pytest.mark.parametrize("tag", ["s8", "s64"])
+@pytest.mark.parametrize("att", [1, 2, 3])
+@pytest.mark.parametrize("gnn", ["AT", "SAGE", "GCN"])
+def test_layer_vs_reference_golden(tag, att, gnn):
+    g = load("layer_" + tag)
+    k = "a%d_%s_" % (att, gnn)
+    x = t(g["x"]).to(DEV).requires_grad_(True)
+    n, fin = x.shape
+    dd = g[k + "out"].shape[1]
+    lay = make_layer(g, k, fin, dd, att, gnn)
+    adj = cuda_adj(n, g["indices"])
+    aux = [t(g["aux0"]).to(DEV), t(g["aux1"]).to(DEV)]
+    out, e, au = lay(x, adj, aux)
+    assert_close(out.cpu(), g[k + "out"], RT, "out")
+    assert_close(e.cpu(), g[k + "edge_e"], RT, "edge_e")
+    assert_close(au[0].cpu(), g[k + "aux0"], RT, "aux0")
+    assert_close(au[1].cpu(), g[k + "aux1"], RT, "aux1")
+    loss = (out * t(g["r_out"]).to(DEV)).sum() + (e * t(g["r_e"]).to(DEV)).sum() \
+        + (au[0] * t(g["r_aux0"]).to(DEV)).sum() + (au[1] * t(g["r_aux1"]).to(DEV)).sum()
+    loss.backward()
+    assert_close(x.grad.cpu(), g[k + "gx"], RT_GRAD, "gx")
+    for name, prm in lay.named_parameters():
+        if k + "g." + name in g:
+            assert_close(prm.grad.cpu(), g[k + "g." + name], RT_GRAD, "g." + name)
+        else:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
+
+
+# ------------------------------------------------------------------ model vs reference golden
+MODEL_TAGS = ["model_a3_AT", "model_a1_SAGE", "model_a2_GCN", "model_a3_AT_res"]
+
+
+def model_from_golden(tag):
+    from edgedisentangle_ssl_b200.utils import get_parser
+    g = load(tag)
+    args = get_parser().parse_args([str(a) for a in g["argv"]])
+    args.cuda, args.hetero = True, True
+    args.size = g["x"].shape[1]
+    enc = edis.DISGAT(args, nfeat=args.size, nhid=args.nhid, nclass=args.nhid, nheads=args.nhead,
+                      dropout=args.dropout)
+    enc.load_state_dict(params_from(g, "enc0."), strict=True)
+    fus = []
+    for i, res in ((1, args.size), (2, args.nhid)):
+        f = edis.FuseLayer(args, args.nhead, nfeat=args.nhid, residue=res if args.residue else 0)
+        f.load_state_dict(params_from(g, "cls0.fuse%d." % i), strict=True)
+        fus.append(f.to(DEV))
+    return g, args, enc.to(DEV), fus
+
+
+@pytest.mark.parametrize("tag", MODEL_TAGS)
+def test_model_traversal_vs_reference_golden(tag):
+    g, args, enc, fus = model_from_golden(tag)
+    enc.eval()
+    x = t(g["x"]).to(DEV)
+    adj = cuda_adj(int(g["n"]), g["indices"])
+    aux = [t(g["aux0"]).to(DEV), t(g["aux1"]).to(DEV)]
+    with torch.no_grad():
+        em = enc.get_em(x, adj, fus)
+        assert_close(em[0].cpu(), g["get_em_1"], RT, "get_em[0]")
+        assert_close(em[1].cpu(), g["get_em_2"], RT, "get_em[1]")
+        assert_close(enc(x, adj, fus).cpu(), g["forward"], RT, "forward")
+        ga = enc.get_adjs(x, adj, fus)
+        pa = enc.predict_adjs_sparse(x, adj, fus, aux)
+        ge = enc.get_edge_em(x, adj, fus)
+    for layer in range(2):
+        assert_close(torch.stack(ga[layer]).cpu(), g["get_adjs"][layer], RT, "get_adjs")
+        assert_close(torch.stack([h[0] for h in pa[layer]]).cpu(), g["pred_aux0"][layer], RT, "aux0")
+        assert_close(torch.stack([h[1] for h in pa[layer]]).cpu(), g["pred_aux1"][layer], RT, "aux1")
+        assert_close(torch.stack(ge[layer]).cpu(), g["edge_em_l%d" % layer], RT, "edge_em")
+
+
+@pytest.mark.parametrize("tag", MODEL_TAGS)
+def test_model_cls_step_grads_vs_reference_golden(tag):
+    """First recorded train step (CLS, dropout 0): loss and encoder / fuser gradients."""
+    g, args, enc, fus = model_from_golden(tag)
+    enc.train()
+    clf = edis.MLP(in_feat=args.nhid, hidden_size=args.nhid, out_size=int(g["labels"].max()) + 1, layers=2)
+    clf.load_state_dict(params_from(g, "cls0.classifier."), strict=True)
+    clf.to(DEV)
+    x, labels = t(g["x"]).to(DEV), t(g["labels"]).to(DEV)
+    adj = cuda_adj(int(g["n"]), g["indices"])
+    out = clf(enc.get_em(x, adj, fus)[-1], cls=True)
+    tr = t(g["cls_idx_train"]).to(DEV)
+    loss = torch.nn.functional.nll_loss(out[tr], labels[tr])
+    assert_close(loss.item(), g["cls.log.loss_train"], RT, "loss_train")
+    loss.backward()
+    checked = 0
+    for name, prm in enc.named_parameters():
+        key = "cls.encgrad." + name
+        if key in g:
+            assert_close(prm.grad.cpu(), g[key], RT_GRAD, key)
+            checked += 1
+    assert checked >= 8
+    for name, prm in fus[0].named_parameters():
+        assert_close(prm.grad.cpu(), g["cls.fuse1grad." + name], RT_GRAD, "fuse1." + name)
+
+
+# ------------------------------------------------------------------ fused channels vs CPU oracle
+def oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux):
+    """Run the oracle per channel; returns outputs and grads in the fused layout."""
+    p = {}
+    for c, l in enumerate(chs):
+        for name, prm in l.named_parameters():
+            p["c%d.%s" % (c, name)] = prm.detach().cpu().clone().requires_grad_(True)
+    x = x_cpu.clone().requires_grad_(True)
+    outs, es, auxs = [], [], []
+    for c in range(len(chs)):
+        o, e, au = od.disga_layer(p, "c%d." % c, x, idx, att, gnn, aux=aux)
+        outs.append(o)
+        es.append(e)
+        auxs.append(au)
+    out = torch.cat(outs, 1)
+    e = torch.cat(es, 1)
+    au = [torch.cat([a_[k] for a_ in auxs], 1) for k in range(len(aux))]
+    loss = (out * r_out).sum() + (e * r_e).sum() + sum((a_ * r).sum() for a_, r in zip(au, r_aux))
+    loss.backward()
+    return out, e, au, x.grad, p
+
+
+CASES = [
+    # (n, m, C, D, F, max_chunk)
+    (300, 2500, 4, 64, 24, 16),     # VecT<2,16>, split rows
+    (257, 1800, 8, 64, 100, 32),    # C=8 (config A shape), F=100
+    (200, 1500, 2, 64, 16, 0),      # VecT<1,16>
+    (150, 900, 3, 20, 10, 8),       # scalar path, odd C, D not multiple of 4... (20 is), ragged
+    (120, 700, 2, 13, 7, 0),        # scalar path, D % 4 != 0
+    (90, 500, 4, 32, 12, 4),        # VecT<1,8>
+    (80, 400, 1, 128, 9, 0),        # VecT<1,32>
+]
+
+
+@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("att", [1, 2, 3])
+@pytest.mark.parametrize("gnn", ["AT", "GCN", "SAGE"])
+def test_fused_channels_vs_oracle(case, att, gnn):
+    n, m, C, D, Fin, max_chunk = case
+    torch.manual_seed(1000 + n + att)
+    idx_np = hub_graph(n, m, seed=n)
+    idx = torch.from_numpy(idx_np)
+    e_cnt = idx.shape[1]
+    chs = [edis.DisGALayer(Fin, D, dropout=0.2, alpha=0.1, att_type=att, gnn_type=gnn) for _ in range(C)]
+    x_cpu = torch.randn(n, Fin)
+    rng = np.random.RandomState(7)
+    aux = [torch.from_numpy(np.sort(rng.randint(0, n * n, 333))).long()]
+    aux = [torch.stack([a_ // n, a_ % n]) for a_ in aux] + [torch.from_numpy(rng.randint(0, n, (2, 65))).long()]
+    r_out, r_e = torch.randn(n, C * D), torch.randn(e_cnt, C)
+    r_aux = [torch.randn(a_.shape[1], C) for a_ in aux]
+    o_ref, e_ref, au_ref, gx_ref, p_ref = oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux)
+
+    for l in chs:
+        l.to(DEV).eval()
+    graph = edis.Graph(n, idx_np[0], idx_np[1], device=DEV, max_chunk=max_chunk)
+    x = x_cpu.to(DEV).requires_grad_(True)
+    out, e, au = run_channels(chs, x, graph, [a_.to(DEV) for a_ in aux])
+    assert_close(out.cpu(), o_ref, RT, "out")
+    assert_close(e.cpu(), e_ref, RT, "edge_e")
+    for k in range(2):
+        assert_close(au[k].cpu(), au_ref[k], RT, "aux%d" % k)
+    loss = (out * r_out.to(DEV)).sum() + (e * r_e.to(DEV)).sum() + sum((a_ * r.to(DEV)).sum() for a_, r in zip(au, r_aux))
+    loss.backward()
+    assert_close(x.grad.cpu(), gx_ref, RT_GRAD, "gx")
+    for c, l in enumerate(chs):
+        for name, prm in l.named_parameters():
+            ref = p_ref["c%d.%s" % (c, name)].grad
+            if ref is None:
+                assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
+            else:
+                assert_close(prm.grad.cpu(), ref, RT_GRAD, "c%d.%s" % (c, name))
+
+
+def test_isolated_rows_and_empty_pairs():
+    """Rows without in-edges aggregate to 0 (elu(0) = 0); an empty pair list is legal."""
+    n, C, D, Fin = 40, 2, 64, 8
+    rows = np.array([0, 0, 3, 5, 5, 5], dtype=np.int64)
+    cols = np.array([1, 2, 3, 0, 5, 7], dtype=np.int64)
+    graph = edis.Graph(n, rows, cols, device=DEV)
+    chs = [edis.DisGALayer(Fin, D, 0.0, 0.1, att_type=3, gnn_type="AT").to(DEV).eval() for _ in range(C)]
+    x = torch.randn(n, Fin, device=DEV, requires_grad=True)
+    empty = torch.zeros(2, 0, dtype=torch.int64, device=DEV)
+    out, e, au = run_channels(chs, x, graph, [empty])
+    assert au[0].shape == (0, C) and e.shape == (6, C)
+    mask = torch.ones(n, dtype=torch.bool)
+    mask[[0, 3, 5]] = False
+    assert float(out[mask.to(DEV)].abs().max()) == 0.0
+    out.sum().backward()
+    assert torch.isfinite(x.grad).all()
+
+
+# ------------------------------------------------------------------ dropout (train mode)
+def fused(graph, att, C, D, P, Q, a, V, training=False, p=0.0, seed=0):
+    """DisGAFused on explicit operands (builds the [N, W] projection block the op expects)."""
+    CD = C * D
+    if att == 3:
+        proj, offs = torch.cat([P, Q, V], 1), (0, CD, 2 * CD)
+    else:
+        proj, offs = torch.cat([P, V], 1), (0, 0, CD)
+    return Fn.DisGAFused.apply(graph, att, C, D, proj, offs[0], offs[1], offs[2], None, None, a, None,
+                               training, p, seed)
+
+
+def test_dropout_is_reproducible_and_consistent_between_fwd_and_bwd():
+    n, m, C, D = 300, 3000, 4, 64
+    idx_np = hub_graph(n, m, seed=3)
+    graph = edis.Graph(n, idx_np[0], idx_np[1], device=DEV, max_chunk=32)
+    torch.manual_seed(0)
+    P, Q, V = (torch.randn(n, C * D, device=DEV) for _ in range(3))
+    a = torch.randn(C, D, device=DEV)
+    V = V.requires_grad_(True)
+    o1, _ = fused(graph, 3, C, D, P, Q, a, V, True, 0.5, 1234)
+    o2, _ = fused(graph, 3, C, D, P, Q, a, V, True, 0.5, 1234)
+    o3, _ = fused(graph, 3, C, D, P, Q, a, V, True, 0.5, 99)
+    o_eval, _ = fused(graph, 3, C, D, P, Q, a, V, False, 0.5, 0)
+    assert torch.equal(o1, o2) and not torch.equal(o1, o3) and not torch.equal(o1, o_eval)
+    # same mask in fwd and bwd: directional derivative wrt V (finite differences, fixed seed)
+    r = torch.randn(n, C * D, device=DEV)
+    (gV,) = torch.autograd.grad((o1 * r).sum(), V)
+    dV = torch.randn_like(V)
+    eps = 1e-3
+    op, _ = fused(graph, 3, C, D, P, Q, a, (V + eps * dV).detach(), True, 0.5, 1234)
+    om, _ = fused(graph, 3, C, D, P, Q, a, (V - eps * dV).detach(), True, 0.5, 1234)
+    fd = (((op - om) * r).sum() / (2 * eps)).item()
+    an = (gV * dV).sum().item()
+    assert abs(fd - an) <= 5e-3 * max(1.0, abs(an)), (fd, an)
+    # keep rate: E[alpha_drop] = alpha  ->  the train-mode aggregate is an unbiased estimate
+    ones = torch.ones(n, C * D, device=DEV)
+    outs = torch.stack([fused(graph, 2, C, D, P, P, None, ones, True, 0.5, s)[0] for s in range(24)]).mean(0)
+    assert abs(outs.mean().item() - 1.0) < 0.02     # elu(1) = 1 when every V row is all-ones
+
+
+# ------------------------------------------------------------------ SSL ops
+@pytest.mark.parametrize("cs", [1, 4, 8])
+def test_ssl_wmse_vs_oracle(cs):
+    torch.manual_seed(cs)
+    m = 5000
+    s = torch.randn(m, cs)
+    tgt = (torch.rand(m) < 0.11).float()
+    s_ref = s.clone().requires_grad_(True)
+    ref = od.adj_mse_loss(torch.sigmoid(s_ref.sum(1)), tgt)
+    ref.backward()
+    sg = s.to(DEV).requires_grad_(True)
+    loss = Fn.SslWmse.apply(sg, tgt.to(DEV), int((tgt != 0).sum()))
+    assert_close(loss.item(), ref.item(), RT, "wmse")
+    (loss * 3.0).backward()
+    assert_close(sg.grad.cpu(), 3.0 * s_ref.grad, RT, "wmse grad")
+
+
+def test_ssl_wmse_vs_reference_golden():
+    g = load("loss_small")
+    pred = t(g["pred"])
+    logit = torch.log(pred / (1 - pred)).unsqueeze(1).to(DEV)   # sigmoid^-1, one channel
+    tgt = t(g["tgt"]).to(DEV)
+    loss = Fn.SslWmse.apply(logit, tgt, int((tgt != 0).sum()))
+    assert_close(loss.item(), float(g["loss"]), 1e-5, "adj_mse_loss golden")
+
+
+@pytest.mark.parametrize("k", [4, 8])
+def test_nll_const_label_vs_torch(k):
+    torch.manual_seed(k)
+    n = 3001
+    z = torch.randn(n, k) * 3
+    for label in (0, k - 1):
+        z_ref = z.clone().requires_grad_(True)
+        ref = torch.nn.functional.nll_loss(torch.log_softmax(z_ref, 1), torch.full((n,), label))
+        ref.backward()
+        zg = z.to(DEV).requires_grad_(True)
+        loss = Fn.NllConstLabel.apply(zg, label)
+        assert_close(loss.item(), ref.item(), RT, "nll")
+        loss.backward()
+        assert_close(zg.grad.cpu(), z_ref.grad, RT, "nll grad")
+
+
+@pytest.mark.parametrize("tag", ["s8", "s64"])
+def test_sp_ops_vs_reference_golden(tag):
+    from edgedisentangle_ssl_b200 import utils as U
+    g = load("layer_" + tag)
+    idx = t(g["indices"]).to(DEV)
+    vals = t(g["spmm_vals"]).to(DEV).requires_grad_(True)
+    mat = t(g["spmm_mat"]).to(DEV).requires_grad_(True)
+    n = int(g["n"])
+    out = U.sp_matmul(idx, vals, mat)
+    assert_close(out.cpu(), g["spmm_out"], RT, "sp_matmul")
+    sm = U.sp_softmax(idx, vals, n)
+    assert_close(sm.cpu(), g["spsm_out"], RT, "sp_softmax")
+    # gradients vs the oracle's autograd
+    r1, r2 = torch.randn(out.shape), torch.randn(sm.shape)
+    ((out * r1.to(DEV)).sum() + (sm * r2.to(DEV)).sum()).backward()
+    v_ref = t(g["spmm_vals"]).clone().requires_grad_(True)
+    m_ref = t(g["spmm_mat"]).clone().requires_grad_(True)
+    ic = t(g["indices"])
+    ((od.sp_matmul(ic, v_ref, m_ref) * r1).sum() + (od.sp_softmax(ic, v_ref, n) * r2).sum()).backward()
+    assert_close(vals.grad.cpu(), v_ref.grad, RT_GRAD, "g values")
+    assert_close(mat.grad.cpu(), m_ref.grad, RT_GRAD, "g mat")
+
+
+# ------------------------------------------------------------------ size-independent properties
+def test_large_graph_properties():
+    """2M-edge power-law graph, C=8, D=64: softmax rows sum to one (all-ones V -> out == 1),
+    the aggregate is linear in V, and the source pass is the exact adjoint of the forward."""
+    from edgedisentangle_ssl_b200.synthetic import power_law_graph
+    n, C, D = 100_000, 8, 64
+    idx = power_law_graph(n, 1_000_000, seed=5)
+    graph = edis.Graph(n, idx[0], idx[1], device=DEV)
+    assert graph.info["max_in"] > 1000
+    torch.manual_seed(0)
+    P = torch.randn(n, C * D, device=DEV) * 0.3
+    Q = torch.randn(n, C * D, device=DEV) * 0.3
+    a = torch.randn(C, D, device=DEV) * 0.3
+    ones = torch.ones(n, C * D, device=DEV)
+    out, e = fused(graph, 3, C, D, P, Q, a, ones)
+    assert float((out - 1).abs().max()) < 2e-6
+    V1, V2 = torch.randn(n, C * D, device=DEV), torch.randn(n, C * D, device=DEV)
+    pos = lambda V: fused(graph, 3, C, D, P, Q, a, V)  # noqa: E731
+    # inverse-elu makes the comparison linear: compare pre-activations via positive shifts
+    big = 50.0
+    o1, _ = pos(V1 + big)
+    o2, _ = pos(V2 + big)
+    o12, _ = pos(V1 + V2 + big)
+    assert float(((o1 - big) + (o2 - big) - (o12 - big)).abs().max()) < 2e-4
+    # adjoint: <A V, R> == <V, A^T R>
+    Vg = V1.clone().requires_grad_(True)
+    o, _ = pos(Vg + big)
+    R = torch.randn_like(o)
+    (gV,) = torch.autograd.grad((o * R).sum(), Vg)
+    lhs = ((o - big) * R).sum().double().item()
+    rhs = (gV * V1).sum().double().item()
+    assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0), (lhs, rhs)
