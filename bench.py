@@ -48,6 +48,7 @@ def parse():
     ap.add_argument("--cpu-raw-edges", type=int, default=150_000, help="CPU-baseline sample: raw edge draws")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--max-chunk", type=int, default=0)
+    ap.add_argument("--graph-cache", default=None, help="npy file caching the generated graph (tuning sweeps)")
     return ap.parse_args()
 
 
@@ -208,7 +209,12 @@ def main():
     # ---- workload (weak scaling: every rank owns a graph of the same size) -------------------
     t0 = time.time()
     if world == 1:
-        idx = power_law_graph(a.nodes, a.raw_edges, seed=0)
+        if a.graph_cache and os.path.exists(a.graph_cache):
+            idx = np.load(a.graph_cache)
+        else:
+            idx = power_law_graph(a.nodes, a.raw_edges, seed=0)
+            if a.graph_cache:
+                np.save(a.graph_cache, idx)
         graph = edis.Graph(a.nodes, idx[0], idx[1], device=dev, max_chunk=a.max_chunk)
         n_local, n_total, e_local = a.nodes, a.nodes, graph.e
         del idx

@@ -8,7 +8,8 @@ import os
 from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libedis.so")
+# EDIS_LIB: alternative build of the same library (tuning variants); default is the in-tree one
+LIB_PATH = os.environ.get("EDIS_LIB") or os.path.join(_PKG, "libedis.so")
 
 
 class EdisError(RuntimeError):
@@ -54,6 +55,7 @@ SIGNATURES = {
     "edis_graph_workspace_bytes": (c_int64, [c_void_p, c_int64]),
     "edis_disga_fwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P,
                                _P, _P, _P, _P, _P, c_int64, _P]),
+    "edis_disga_rec_bytes": (c_int64, [c_void_p, _descp]),
     "edis_disga_bwd": (c_int, _BWD_ARGS),
     "edis_disga_bwd_dst": (c_int, _BWD_ARGS),
     "edis_disga_bwd_src": (c_int, _BWD_ARGS),

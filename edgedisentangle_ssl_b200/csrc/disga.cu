@@ -18,6 +18,21 @@
 #include "edis_common.cuh"
 #include "traits.cuh"
 
+// Tuning knobs (build-time): edges in flight per warp for the 128-bit paths and the minimum
+// resident CTAs per SM the register allocator must allow.
+#ifndef EDIS_U_KV1
+#define EDIS_U_KV1 4
+#endif
+#ifndef EDIS_U_KV2
+#define EDIS_U_KV2 2
+#endif
+#ifndef EDIS_U_KV4
+#define EDIS_U_KV4 1
+#endif
+#ifndef EDIS_MINB
+#define EDIS_MINB 2
+#endif
+
 namespace edis {
 
 struct LayerArgs {
@@ -34,6 +49,7 @@ struct LayerArgs {
   // backward
   const float *g_out, *g_edge_e;
   float *gP, *gQ, *ga, *gV, *edge_rec, *gh;
+  unsigned char* esign;              // att 3: sign bits of P_i + Q_j per edge (dst pass -> src pass)
   int64_t ldgp, ldgq, ldgv;          // row strides of gP, gQ, gV
   float* partial;
   int64_t pwidth;
@@ -56,7 +72,7 @@ __device__ __forceinline__ void store_x(float* base, const float (&x)[RX > 0 ? R
 
 // ------------------------------------------------------------------ forward
 template <class T, int ATT, int RX, int U>
-__global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
+__global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
   const int lane = threadIdx.x & 31;
@@ -68,37 +84,28 @@ __global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
     const Item it = A.items[item_id];
     const int c0 = grp * CPW;
     const int off = c0 * A.D;
-    int cidx[NCH];
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
-    float pr[R], ar[R], sd[NCH];
-    if (ATT >= 2) T::load(pr, A.P + static_cast<int64_t>(it.row) * A.ldp + off, lane, A.D);
+    const int myc = c0 + T::own_ch(lane);   // the channel whose scalar math this lane owns
+    const int64_t srow = static_cast<int64_t>(it.row);
+    float pr[R], ar[R], sd = 0.0f;
+    if (ATT >= 2) T::load(pr, A.P + srow * A.ldp + off, lane, A.D);
     if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
-    if (ATT == 1) {
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) sd[k] = __ldg(A.P + static_cast<int64_t>(it.row) * A.ldp + cidx[k]);
-    }
-    float acc[R], accx[NACC], ws[NCH], wms[NCH];
+    if (ATT == 1) sd = __ldg(A.P + srow * A.ldp + myc);
+    float acc[R], accx[NACC], ws = 0.0f, wms = 0.0f;
     zero<T>(acc);
 #pragma unroll
     for (int k = 0; k < NACC; ++k) accx[k] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) ws[k] = wms[k] = 0.0f;
 
     for (int eb = it.beg; eb < it.end; eb += 32) {
       const int cnt = min(32, it.end - eb);
       const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
       for (int t = 0; t < cnt; t += U) {
-        float q[U][R], h[U][R], qs[U][NCH], xj[U][RXA];
+        float q[U][R], h[U][R], qs[U], xj[U][RXA];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
             const int64_t j = __shfl_sync(FULL, myj, t + u);
             if (ATT >= 2) T::load(q[u], A.Q + j * A.ldq + off, lane, A.D);
-            if (ATT == 1) {
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) qs[u][k] = __ldg(A.Q + j * A.ldq + cidx[k]);
-            }
+            if (ATT == 1) qs[u] = __ldg(A.Q + j * A.ldq + myc);
             if (RX == 0) T::load(h[u], A.V + j * A.ldv + off, lane, A.D);
             else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
           }
@@ -107,10 +114,9 @@ __global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
             const int64_t edge = eb + t + u;
-            float e[NCH];
+            float e;
             if (ATT == 1) {
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) e[k] = sd[k] + qs[u][k];
+              e = sd + qs[u];
             } else {
               float part[NCH];
 #pragma unroll
@@ -120,49 +126,48 @@ __global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
                 if (ATT == 3) part[r / RPC] = fmaf(ar[r], lrelu01(pr[r] + q[u][r]), part[r / RPC]);
                 else part[r / RPC] = fmaf(pr[r], q[u][r], part[r / RPC]);
               }
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) e[k] = T::reduce(part[k]);
+              e = T::reduce_own(part, lane);
             }
-            float wm[NCH];
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              const float w = __expf(sigmoidf_fast(e[k]));
-              const float ms = A.training ? keep_scale(A.seed, edge * A.C + cidx[k], A.p, A.inv_keep) : 1.0f;
-              wm[k] = w * ms;
-              ws[k] += w;
-              wms[k] += wm[k];
-            }
+            const float w = __expf(sigmoidf_fast(e));
+            const float ms = A.training ? keep_scale(A.seed, edge * A.C + myc, A.p, A.inv_keep) : 1.0f;
+            const float wm = w * ms;
+            ws += w;
+            wms += wm;
             if (RX == 0) {
 #pragma unroll
-              for (int r = 0; r < R; ++r) acc[r] = fmaf(wm[r / RPC], h[u][r], acc[r]);
+              for (int k = 0; k < NCH; ++k) {
+                const float wk = T::from_owner(wm, k, lane);
+#pragma unroll
+                for (int r = k * RPC; r < (k + 1) * RPC; ++r) acc[r] = fmaf(wk, h[u][r], acc[r]);
+              }
             } else {
 #pragma unroll
               for (int cc = 0; cc < CPW; ++cc) {
-                const float wcc = T::bcast(wm, cc);
+                const float wcc = T::from_channel(wm, cc);
 #pragma unroll
                 for (int k = 0; k < RX; ++k) accx[cc * RXA + k] = fmaf(wcc, xj[u][k], accx[cc * RXA + k]);
               }
             }
-            if (T::writer(lane)) {
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) A.edge_e[edge * A.C + cidx[k]] = e[k];
-            }
+            if (T::own_writer(lane)) A.edge_e[edge * A.C + myc] = e;
           }
         }
       }
     }
-    const int64_t srow = static_cast<int64_t>(it.row);
     if (RX == 0) {
       if (it.slot < 0) {
         float o[R], hp[R], br[R];
         if (A.bias) T::load(br, A.bias + off, lane, A.D);
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
-          const float wsum = ws[r / RPC];
-          float v = wsum > 0.0f ? acc[r] / wsum : 0.0f;
-          if (A.bias) v += br[r];
-          hp[r] = v;
-          o[r] = v > 0.0f ? v : expm1f(v);
+        for (int k = 0; k < NCH; ++k) {
+          const float wsum = T::from_owner(ws, k, lane);
+          const float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
+#pragma unroll
+          for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+            float v = acc[r] * inv;
+            if (A.bias) v += br[r];
+            hp[r] = v;
+            o[r] = v > 0.0f ? v : expm1f(v);
+          }
         }
         T::store(A.hpre + srow * A.C * A.D + off, hp, lane, A.D);
         T::store(A.out + srow * A.C * A.D + off, o, lane, A.D);
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
       // SAGE: neigh = agg / (rowsum(alpha_drop) + 1) = acc / (sum w*mask + sum w)
 #pragma unroll
       for (int cc = 0; cc < CPW; ++cc) {
-        const float den = T::bcast(ws, cc) + T::bcast(wms, cc);
+        const float den = T::from_channel(ws, cc) + T::from_channel(wms, cc);
         float o[RXA];
 #pragma unroll
         for (int k = 0; k < RX; ++k)
@@ -183,14 +188,11 @@ __global__ void __launch_bounds__(256) k_disga_fwd(const LayerArgs A) {
         store_x<RX>(dst, o, lane, A.F);
       }
     }
-    if (T::writer(lane)) {
+    if (T::own_writer(lane)) {
       const int aggw = RX == 0 ? A.C * A.D : A.C * A.F;
       float* st = it.slot < 0 ? A.stats + srow * 2 * A.C : A.partial + static_cast<int64_t>(it.slot) * A.pwidth + aggw;
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        st[cidx[k]] = ws[k];
-        st[A.C + cidx[k]] = wms[k];
-      }
+      st[myc] = ws;
+      st[A.C + myc] = wms;
     }
   }
 }
@@ -246,9 +248,10 @@ __global__ void k_combine_rows(const SplitRow* split, int64_t n_split, const flo
 // d logit = alpha (d alpha - t) * s(1-s) [+ g_edge_e]; accumulates dP_i (registers) and da
 // (registers, flushed with vector atomics once per warp).
 template <class T, int ATT, int RX, int U>
-__global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
+__global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
+  constexpr int SBPL = (R + 7) / 8;   // sign bytes per lane per edge
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -267,20 +270,15 @@ __global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
       zero<T>(da);
       da_grp = grp;
     }
-    int cidx[NCH];
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
+    const int myc = c0 + T::own_ch(lane);
     const int64_t srow = static_cast<int64_t>(it.row);
     const int64_t rowoff = srow * CD + off;
     // every chunk of a split row computes the same gh; the first chunk (or the only one) stores it
     bool first_chunk = it.slot < 0;
     if (it.slot >= 0) first_chunk = item_id == 0 || A.items[item_id - 1].row != it.row;
-    float dh[R], dhx[NACC], tc[NCH], inv[NCH];
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) {
-      const float wsum = __ldg(A.stats + srow * 2 * A.C + cidx[k]);
-      inv[k] = wsum > 0.0f ? 1.0f / wsum : 0.0f;
-    }
+    float dh[R], dhx[NACC], tc = 0.0f;
+    const float wsum = __ldg(A.stats + srow * 2 * A.C + myc);
+    const float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
     if (RX == 0) {
       float go[R], hp[R], br[R], tpart[NCH];
       T::load(go, A.g_out + rowoff, lane, A.D);
@@ -294,21 +292,14 @@ __global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
         const float agg = A.bias ? hp[r] - br[r] : hp[r];
         tpart[r / RPC] = fmaf(dh[r], agg, tpart[r / RPC]);
       }
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) tc[k] = T::reduce(tpart[k]);
       if (first_chunk) T::store(A.gh + rowoff, dh, lane, A.D);
+      tc = T::reduce_own(tpart, lane);
     } else {
       // SAGE: div = rowsum(alpha_drop) + 1 = (sum w*mask + sum w) / sum w, detached (layers.py:103)
-      float wmsv[NCH], wsv[NCH], tmine[NCH];
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) {
-        wsv[k] = __ldg(A.stats + srow * 2 * A.C + cidx[k]);
-        wmsv[k] = __ldg(A.stats + srow * 2 * A.C + A.C + cidx[k]);
-        tmine[k] = 0.0f;
-      }
+      const float wmsv = __ldg(A.stats + srow * 2 * A.C + A.C + myc);
 #pragma unroll
       for (int cc = 0; cc < CPW; ++cc) {
-        const float wsc = T::bcast(wsv, cc), den = wsc + T::bcast(wmsv, cc);
+        const float wsc = T::from_channel(wsum, cc), den = wsc + T::from_channel(wmsv, cc);
         const float rdiv = den > 0.0f ? wsc / den : 0.0f;   // 1 / div
         float gn[RXA], ng[RXA], o[RXA];
         load_x<RX>(gn, A.g_out + (srow * A.C + c0 + cc) * A.F, lane, A.F);
@@ -321,27 +312,21 @@ __global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
           tp = fmaf(gn[k], ng[k], tp);     // <g_agg, agg> = <g_neigh, neigh>
         }
         tp = warp_sum(tp);
-#pragma unroll
-        for (int k = 0; k < NCH; ++k)
-          if (T::ch(k, lane) == cc) tmine[k] = tp;
+        if (T::own_ch(lane) == cc) tc = tp;
         if (first_chunk) store_x<RX>(A.gh + (srow * A.C + c0 + cc) * A.F, o, lane, A.F);
       }
-#pragma unroll
-      for (int k = 0; k < NCH; ++k) tc[k] = tmine[k];
     }
 
-    float pr[R], ar[R], dP[R], dsd[NCH];
+    float pr[R], ar[R], dP[R], dsd = 0.0f;
     if (ATT >= 2) T::load(pr, A.P + srow * A.ldp + off, lane, A.D);
     if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
     zero<T>(dP);
-#pragma unroll
-    for (int k = 0; k < NCH; ++k) dsd[k] = 0.0f;
 
     for (int eb = it.beg; eb < it.end; eb += 32) {
       const int cnt = min(32, it.end - eb);
       const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
       for (int t = 0; t < cnt; t += U) {
-        float q[U][R], h[U][R], ev[U][NCH], gx[U][NCH], xj[U][RXA];
+        float q[U][R], h[U][R], ev[U], gx[U], xj[U][RXA];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
@@ -350,83 +335,86 @@ __global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
             if (ATT >= 2) T::load(q[u], A.Q + j * A.ldq + off, lane, A.D);
             if (RX == 0) T::load(h[u], A.V + j * A.ldv + off, lane, A.D);
             else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              ev[u][k] = __ldg(A.edge_e + edge * A.C + cidx[k]);
-              gx[u][k] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + cidx[k]) : 0.0f;
-            }
+            ev[u] = __ldg(A.edge_e + edge * A.C + myc);
+            gx[u] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + myc) : 0.0f;
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
             const int64_t edge = eb + t + u;
-            float gdot[NCH];
+            float gdot = 0.0f;
             if (RX == 0) {
               float gpart[NCH];
 #pragma unroll
               for (int k = 0; k < NCH; ++k) gpart[k] = 0.0f;
 #pragma unroll
               for (int r = 0; r < R; ++r) gpart[r / RPC] = fmaf(dh[r], h[u][r], gpart[r / RPC]);
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) gdot[k] = T::reduce(gpart[k]);
+              gdot = T::reduce_own(gpart, lane);
             } else {
-#pragma unroll
-              for (int k = 0; k < NCH; ++k) gdot[k] = 0.0f;
 #pragma unroll
               for (int cc = 0; cc < CPW; ++cc) {
                 float gp = 0.0f;
 #pragma unroll
                 for (int k = 0; k < RX; ++k) gp = fmaf(dhx[cc * RXA + k], xj[u][k], gp);
                 gp = warp_sum(gp);
-#pragma unroll
-                for (int k = 0; k < NCH; ++k)
-                  if (T::ch(k, lane) == cc) gdot[k] = gp;
+                if (T::own_ch(lane) == cc) gdot = gp;
               }
             }
-            float de[NCH];
-#pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              const float s = sigmoidf_fast(ev[u][k]);
-              const float alpha = __expf(s) * inv[k];
-              const float ms = A.training ? keep_scale(A.seed, edge * A.C + cidx[k], A.p, A.inv_keep) : 1.0f;
-              const float ds = alpha * (gdot[k] * ms - tc[k]);
-              de[k] = fmaf(ds, s * (1.0f - s), gx[u][k]);
-              if (T::writer(lane)) {
-                A.edge_rec[edge * 2 * A.C + cidx[k]] = alpha * ms;
-                A.edge_rec[edge * 2 * A.C + A.C + cidx[k]] = de[k];
-              }
-              if (ATT == 1) dsd[k] += de[k];
+            const float s = sigmoidf_fast(ev[u]);
+            const float alpha = __expf(s) * inv;
+            const float ms = A.training ? keep_scale(A.seed, edge * A.C + myc, A.p, A.inv_keep) : 1.0f;
+            const float ds = alpha * (gdot * ms - tc);
+            const float de = fmaf(ds, s * (1.0f - s), gx[u]);
+            if (T::own_writer(lane)) {
+              A.edge_rec[edge * 2 * A.C + myc] = alpha * ms;
+              A.edge_rec[edge * 2 * A.C + A.C + myc] = de;
             }
-            if (ATT == 3) {
+            if (ATT == 1) dsd += de;
+            if (ATT >= 2) {
+              unsigned mask = 0u;
 #pragma unroll
-              for (int r = 0; r < R; ++r) {
-                const float z = pr[r] + q[u][r];
-                const float d = de[r / RPC];
-                dP[r] = fmaf(d * ar[r], z > 0.0f ? 1.0f : 0.01f, dP[r]);
-                da[r] = fmaf(d, lrelu01(z), da[r]);
+              for (int k = 0; k < NCH; ++k) {
+                const float d = T::from_owner(de, k, lane);
+                const float d001 = 0.01f * d;
+#pragma unroll
+                for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+                  if (ATT == 3) {
+                    // dP accumulates U = sum_j de_ij lrelu'(z_ijd); scaled by a once per row
+                    const bool pos = pr[r] + q[u][r] > 0.0f;
+                    dP[r] += pos ? d : d001;
+                    if (pos) mask |= 1u << r;
+                  } else {
+                    dP[r] = fmaf(d, q[u][r], dP[r]);
+                  }
+                }
               }
-            } else if (ATT == 2) {
-#pragma unroll
-              for (int r = 0; r < R; ++r) dP[r] = fmaf(de[r / RPC], q[u][r], dP[r]);
+              if (ATT == 3) {
+                // 1 bit per element: the source pass needs lrelu'(P_i + Q_j), not P_i itself
+                const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
+                if (SBPL == 1) A.esign[so] = static_cast<unsigned char>(mask);
+                else *reinterpret_cast<unsigned short*>(A.esign + so) = static_cast<unsigned short>(mask);
+              }
             }
           }
         }
       }
     }
+    if (ATT == 3) {
+      // lrelu(z) = lrelu'(z) z  =>  da_d = sum_i P_i[d] U_i[d] + sum_j Q_j[d] U'_j[d]: per ROW, not per edge
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        da[r] = fmaf(pr[r], dP[r], da[r]);
+        dP[r] *= ar[r];
+      }
+    }
     if (it.slot < 0) {
       if (ATT >= 2) T::store(A.gP + srow * A.ldgp + off, dP, lane, A.D);
-      if (ATT == 1 && T::writer(lane)) {
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) A.gP[srow * A.ldgp + cidx[k]] = dsd[k];
-      }
+      if (ATT == 1 && T::own_writer(lane)) A.gP[srow * A.ldgp + myc] = dsd;
     } else {
       float* pb = A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
       if (ATT >= 2) T::store(pb + off, dP, lane, A.D);
-      if (ATT == 1 && T::writer(lane)) {
-#pragma unroll
-        for (int k = 0; k < NCH; ++k) pb[cidx[k]] = dsd[k];
-      }
+      if (ATT == 1 && T::own_writer(lane)) pb[myc] = dsd;
     }
   }
   if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
@@ -434,28 +422,34 @@ __global__ void __launch_bounds__(256) k_disga_bwd_dst(const LayerArgs A) {
 
 // ------------------------------------------------------------------ backward, source pass
 // Per source row j over its out-edges (CSC): dV_j = sum_i alpha_drop_ij gh_i (HASV),
-// dQ_j = sum_i d logit_ij * d e_ij / d Q_j.  Pull: gathers gh_i (and P_i), no atomics.
+// dQ_j = sum_i d logit_ij * d e_ij / d Q_j.  Pull: gathers gh_i (and, for att 2, P_i), no atomics
+// on node tensors.  att 3 reads the 1-bit-per-element sign record of the dst pass instead of P_i.
 template <class T, int ATT, bool HASV, int U>
-__global__ void __launch_bounds__(256) k_disga_bwd_src(const LayerArgs A) {
+__global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
+  constexpr int SBPL = (R + 7) / 8;
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int CD = A.C * A.D;
+  float da[R];
+  zero<T>(da);
+  int da_grp = -1;
   for (; unit < A.n_units; unit += nwarps) {
     const int64_t item_id = unit / A.G;
     const int grp = static_cast<int>(unit - item_id * A.G);
     const Item it = A.items[item_id];
     const int c0 = grp * CPW;
     const int off = c0 * A.D;
+    if (ATT == 3 && grp != da_grp) {
+      if (da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
+      zero<T>(da);
+      da_grp = grp;
+    }
     int cidx[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
-    float qr[R], ar[R], accV[R], accQ[R], dss[NCH];
-    if (ATT == 3) {
-      T::load(qr, A.Q + static_cast<int64_t>(it.row) * A.ldq + off, lane, A.D);
-      T::load(ar, A.a + off, lane, A.D);
-    }
+    float accV[R], accQ[R], dss[NCH];
     zero<T>(accV);
     zero<T>(accQ);
 #pragma unroll
@@ -466,12 +460,18 @@ __global__ void __launch_bounds__(256) k_disga_bwd_src(const LayerArgs A) {
       const int mye = lane < cnt ? __ldg(A.eid + eb + lane) : 0;
       for (int t = 0; t < cnt; t += U) {
         float pg[U][R], dh[U][R], ad[U][NCH], de[U][NCH];
+        unsigned sg[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
             const int64_t i = __shfl_sync(FULL, myi, t + u);
             const int64_t edge = __shfl_sync(FULL, mye, t + u);
-            if (ATT >= 2) T::load(pg[u], A.P + i * A.ldp + off, lane, A.D);
+            if (ATT == 2) T::load(pg[u], A.P + i * A.ldp + off, lane, A.D);
+            if (ATT == 3) {
+              const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
+              sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
+                                : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
+            }
             if (HASV) T::load(dh[u], A.gh + i * CD + off, lane, A.D);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
@@ -484,24 +484,30 @@ __global__ void __launch_bounds__(256) k_disga_bwd_src(const LayerArgs A) {
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-              if (HASV) accV[r] = fmaf(ad[u][r / RPC], dh[u][r], accV[r]);
-              if (ATT == 3) {
-                const float z = pg[u][r] + qr[r];
-                accQ[r] = fmaf(de[u][r / RPC] * ar[r], z > 0.0f ? 1.0f : 0.01f, accQ[r]);
-              } else if (ATT == 2) {
-                accQ[r] = fmaf(de[u][r / RPC], pg[u][r], accQ[r]);
-              }
-            }
-            if (ATT == 1) {
+            for (int k = 0; k < NCH; ++k) {
+              const float d = de[u][k], d001 = 0.01f * d;
 #pragma unroll
-              for (int k = 0; k < NCH; ++k) dss[k] += de[u][k];
+              for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+                if (HASV) accV[r] = fmaf(ad[u][k], dh[u][r], accV[r]);
+                if (ATT == 3) accQ[r] += ((sg[u] >> r) & 1u) ? d : d001;
+                else if (ATT == 2) accQ[r] = fmaf(d, pg[u][r], accQ[r]);
+              }
+              if (ATT == 1) dss[k] += d;
             }
           }
         }
       }
     }
-    const int64_t rowoff = static_cast<int64_t>(it.row) * CD + off;
+    if (ATT == 3) {
+      float qr[R], ar[R];
+      T::load(qr, A.Q + static_cast<int64_t>(it.row) * A.ldq + off, lane, A.D);
+      T::load(ar, A.a + off, lane, A.D);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        da[r] = fmaf(qr[r], accQ[r], da[r]);   // source half of da (see the dst pass)
+        accQ[r] *= ar[r];
+      }
+    }
     if (it.slot < 0) {
       if (HASV) T::store(A.gV + static_cast<int64_t>(it.row) * A.ldgv + off, accV, lane, A.D);
       if (ATT >= 2) T::store(A.gQ + static_cast<int64_t>(it.row) * A.ldgq + off, accQ, lane, A.D);
@@ -519,6 +525,7 @@ __global__ void __launch_bounds__(256) k_disga_bwd_src(const LayerArgs A) {
       }
     }
   }
+  if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
 }
 
 // SAGE: gX_j = sum_i sum_c alpha_drop_ij^c gh_i^c.  One warp per source-row chunk, all channels.
@@ -602,10 +609,10 @@ static int launch_layer(Pass pass, const edis_graph* g, const LayerArgs& A, int 
   const int C = A.C, D = A.D;
   static const int kv_env = env_int("EDIS_KV", 0);
   if (D == 64 && C % 2 == 0) {
-    int kv = kv_env ? kv_env : (C % 4 == 0 ? 2 : 1);
-    if (kv == 4 && C % 8 == 0) return launch_att<VecT<4, 16>, 0, 1>(pass, g, A, att, st);
-    if (kv >= 2 && C % 4 == 0) return launch_att<VecT<2, 16>, 0, 2>(pass, g, A, att, st);
-    return launch_att<VecT<1, 16>, 0, 4>(pass, g, A, att, st);
+    int kv = kv_env ? kv_env : (C % 8 == 0 ? 4 : (C % 4 == 0 ? 2 : 1));
+    if (kv == 4 && C % 8 == 0) return launch_att<VecT<4, 16>, 0, EDIS_U_KV4>(pass, g, A, att, st);
+    if (kv >= 2 && C % 4 == 0) return launch_att<VecT<2, 16>, 0, EDIS_U_KV2>(pass, g, A, att, st);
+    return launch_att<VecT<1, 16>, 0, EDIS_U_KV1>(pass, g, A, att, st);
   }
   if (D == 32 && C % 4 == 0) return launch_att<VecT<1, 8>, 0, 4>(pass, g, A, att, st);
   if (D == 128) return launch_att<VecT<1, 32>, 0, 4>(pass, g, A, att, st);
@@ -673,6 +680,15 @@ static int check_ws(const edis_graph* g, int64_t pw, void* workspace, int64_t by
 
 static unsigned nblk(int64_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
+// Layout of the edge scratch `edge_rec`: E x 2C floats (alpha_drop, d logit), then for att 3 the
+// sign records, (C*D-bit masks stored per (edge, channel group, lane)): at most E*C*32 bytes.
+static int64_t rec_float_bytes(const edis_graph* g, const edis_layer_desc* d) {
+  return g->e * 2 * static_cast<int64_t>(d->C) * static_cast<int64_t>(sizeof(float));
+}
+static int64_t rec_total_bytes(const edis_graph* g, const edis_layer_desc* d) {
+  return rec_float_bytes(g, d) + (d->att == 3 ? g->e * static_cast<int64_t>(d->C) * 32 : 0) + 64;
+}
+
 // shared tail of the two backward entry points: score-side source pass + combines
 static int bwd_score_src(const edis_graph* g, const edis_layer_desc* d, LayerArgs& A, bool sage,
                          float* gQ, float* gV, cudaStream_t st) {
@@ -697,6 +713,11 @@ static int bwd_score_src(const edis_graph* g, const edis_layer_desc* d, LayerArg
 }  // namespace edis
 
 using namespace edis;
+
+extern "C" int64_t edis_disga_rec_bytes(const edis_graph* g, const edis_layer_desc* d) {
+  if (!g || !d || d->C < 1) return EDIS_ERR_ARG;
+  return rec_total_bytes(g, d);
+}
 
 extern "C" int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
                               int64_t ldp, const float* Q, int64_t ldq, const float* a,
@@ -757,6 +778,7 @@ static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc
   A.hpre = const_cast<float*>(hpre); A.edge_e = const_cast<float*>(edge_e); A.stats = const_cast<float*>(stats);
   A.g_out = g_out; A.g_edge_e = g_edge_e;
   A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gV; A.edge_rec = edge_rec; A.gh = gh;
+  A.esign = reinterpret_cast<unsigned char*>(edge_rec) + rec_float_bytes(g, d);
   A.ldgp = ldgp; A.ldgq = ldgq; A.ldgv = ldgv;
   A.pwidth = pw;
   if (phases & 1) {
@@ -843,6 +865,7 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
   A.hpre = const_cast<float*>(neigh); A.edge_e = const_cast<float*>(edge_e); A.stats = const_cast<float*>(stats);
   A.g_out = g_neigh; A.g_edge_e = g_edge_e;
   A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gX; A.edge_rec = edge_rec; A.gh = gh;
+  A.esign = reinterpret_cast<unsigned char*>(edge_rec) + rec_float_bytes(g, d);
   A.ldgp = A.ldgq = d->att == 1 ? d->C : CD; A.ldgv = d->Dv;
   A.pwidth = pw;
   A.nbr = g->col;

@@ -33,6 +33,40 @@ struct VecT {
     for (int o = LPC / 2; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
   }
+  // "Owned slot" scheme: after reduce_own every lane holds the channel sum of ONE of its KV
+  // slots (slot own(lane)), so the per-channel scalar math (sigmoid, exp, dropout hash, softmax
+  // backward) is issued once per warp instead of KV times.  Transposed butterfly: KV-1 + log2
+  // (LPC/KV) ... shuffles instead of KV*log2(LPC).
+  static constexpr int SPAN = LPC / KV;   // lanes that end up owning the same slot
+  __device__ static __forceinline__ int own(int lane) { return (lane % LPC) / SPAN; }
+  __device__ static __forceinline__ int own_ch(int lane) { return own(lane) * CPK + lane / LPC; }
+  __device__ static __forceinline__ bool own_writer(int lane) { return (lane % SPAN) == 0; }
+  __device__ static __forceinline__ float reduce_own(float (&v)[NCH], int lane) {
+    int off = LPC / 2;
+#pragma unroll
+    for (int n = KV; n > 1; n >>= 1) {
+      const bool hi = (lane & off) != 0;
+#pragma unroll
+      for (int i = 0; i < n / 2; ++i) {
+        const float keep = hi ? v[i + n / 2] : v[i];
+        const float send = hi ? v[i] : v[i + n / 2];
+        v[i] = keep + __shfl_xor_sync(FULL, send, off);
+      }
+      off >>= 1;
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = SPAN / 2; o > 0; o >>= 1) r += __shfl_xor_sync(FULL, r, o);
+    return r;
+  }
+  // value owned for slot k of this lane's channel group -> this lane
+  __device__ static __forceinline__ float from_owner(float mine, int k, int lane) {
+    return __shfl_sync(FULL, mine, (lane / LPC) * LPC + k * SPAN);
+  }
+  // value owned for warp channel cc (0..CPW) -> every lane
+  __device__ static __forceinline__ float from_channel(float mine, int cc) {
+    return __shfl_sync(FULL, mine, (cc % CPK) * LPC + (cc / CPK) * SPAN);
+  }
   __device__ static __forceinline__ void load(float (&r)[R], const float* base, int lane, int) {
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
@@ -61,6 +95,12 @@ struct ScaT {
   __device__ static __forceinline__ int ch(int, int) { return 0; }
   __device__ static __forceinline__ bool writer(int lane) { return lane == 0; }
   __device__ static __forceinline__ float bcast(const float (&v)[NCH], int) { return v[0]; }
+  __device__ static __forceinline__ int own(int) { return 0; }
+  __device__ static __forceinline__ int own_ch(int) { return 0; }
+  __device__ static __forceinline__ bool own_writer(int lane) { return lane == 0; }
+  __device__ static __forceinline__ float reduce_own(float (&v)[NCH], int) { return reduce(v[0]); }
+  __device__ static __forceinline__ float from_owner(float mine, int, int) { return mine; }
+  __device__ static __forceinline__ float from_channel(float mine, int) { return mine; }
   __device__ static __forceinline__ float reduce(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);

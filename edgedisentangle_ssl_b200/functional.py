@@ -79,6 +79,11 @@ def _desc(att, C, D, training=False, p=0.0, seed=0):
                      seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
 
 
+def _edge_rec(graph, d, device):
+    nbytes = check(lib.edis_disga_rec_bytes(graph.handle, ctypes.byref(d)), "edis_disga_rec_bytes")
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
 def _workspace(graph, width, like):
     nbytes = graph.workspace_bytes(width)
     return torch.empty(nbytes, dtype=torch.uint8, device=like.device), nbytes
@@ -158,7 +163,7 @@ class DisGAFused(torch.autograd.Function):
             else:
                 gQ, ldgq = _off(g_proj, off_q), W
         ga = torch.zeros(C, D, dtype=torch.float32, device=dev) if att == 3 else None
-        edge_rec = torch.empty(e, 2 * C, dtype=torch.float32, device=dev)
+        edge_rec = _edge_rec(graph, d, dev)
         gh = torch.empty(n, CD, dtype=torch.float32, device=dev)
         ws, nbytes = _workspace(graph, 2 * CD + 2 * C, proj)
         args = (graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _off(proj, off_v), ld, _ptr(bias),
@@ -222,7 +227,7 @@ class SageFused(torch.autograd.Function):
         gQ = torch.empty(n, wdt, dtype=torch.float32, device=X.device)
         gX = torch.empty(n, Fin, dtype=torch.float32, device=X.device)
         ga = torch.zeros(C, D, dtype=torch.float32, device=X.device) if att == 3 else None
-        edge_rec = torch.empty(e, 2 * C, dtype=torch.float32, device=X.device)
+        edge_rec = _edge_rec(graph, d, X.device)
         gh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
         ws, nbytes = _workspace(graph, 2 * C * D + 2 * C + Fin, X)
         check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), _ptr(P), ldp, _ptr(Q), ldq, _ptr(a),

@@ -112,8 +112,13 @@ int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d,
  *                  (so they can be column blocks of one gradient buffer of the projection GEMM)
  *   ga[C,D]        grad wrt a (att 3), accumulated with atomics: caller zero-fills
  *   gV[N,C*Dv]     grad wrt V, row stride ldgv (grad wrt bias = column sum of gh; caller reduces)
- *   edge_rec[E,2C] scratch edge tensor (alpha_drop, d logit) handed from the dst pass to the
- *                  src pass;  gh[N,C*Dv] scratch node tensor (grad wrt pre-activation)
+ *   edge_rec       scratch of edis_disga_rec_bytes(g, d) bytes handed from the dst pass to the
+ *                  src pass: per edge (alpha_drop, d logit)[2C] and, for att 3, one SIGN BIT per
+ *                  element of P_i + Q_j (leaky-relu is piecewise linear, so the src pass needs
+ *                  only lrelu'(z): 64 B/edge instead of gathering P_i, 2 KB/edge at C*D=512);
+ *                  gh[N,C*Dv] scratch node tensor (grad wrt pre-activation)
+ *   ga             uses lrelu(z) = lrelu'(z) z: da = sum_i P_i*U_i + sum_j Q_j*U'_j, accumulated per
+ *                  ROW (U = dP / a), so there is no per-edge work for it
  * workspace >= edis_graph_workspace_bytes(g, 2*C*max(D,Dv) + 2*C). */
 int edis_disga_bwd(const edis_graph* g, const edis_layer_desc* d,
                    const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
@@ -123,6 +128,8 @@ int edis_disga_bwd(const edis_graph* g, const edis_layer_desc* d,
                    float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gV, int64_t ldgv,
                    float* edge_rec, float* gh,
                    void* workspace, int64_t workspace_bytes, void* stream);
+/* bytes of the `edge_rec` scratch for this graph / layer (same formula for the SAGE entry) */
+int64_t edis_disga_rec_bytes(const edis_graph* g, const edis_layer_desc* d);
 /* The two passes of edis_disga_bwd as separate calls with the same arguments (dst first, then
  * src on the same stream): destination pass over CSR (gP, ga, gh, edge_rec) and source pass
  * over CSC (gQ, gV).  edis_disga_bwd == both. */

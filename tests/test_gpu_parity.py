@@ -15,7 +15,7 @@ from edgedisentangle_ssl_b200 import functional as Fn
 from edgedisentangle_ssl_b200.layers import run_channels
 from oracle import disgat as od
 from oracle import graph as og
-from helpers import load, t, assert_close, params_from, rel_err
+from helpers import load, t, assert_close, params_from, group_floor
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -100,9 +100,10 @@ def test_layer_vs_reference_golden(tag, att, gnn):
         + (au[0] * t(g["r_aux0"]).to(DEV)).sum() + (au[1] * t(g["r_aux1"]).to(DEV)).sum()
     loss.backward()
     assert_close(x.grad.cpu(), g[k + "gx"], RT_GRAD, "gx")
+    floor = group_floor([v for kk, v in g.items() if kk.startswith(k + "g.")])
     for name, prm in lay.named_parameters():
         if k + "g." + name in g:
-            assert_close(prm.grad.cpu(), g[k + "g." + name], RT_GRAD, "g." + name)
+            assert_close(prm.grad.cpu(), g[k + "g." + name], RT_GRAD, "g." + name, floor)
         else:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
 
@@ -150,6 +151,19 @@ def test_model_traversal_vs_reference_golden(tag):
         assert_close(torch.stack(ge[layer]).cpu(), g["edge_em_l%d" % layer], RT, "edge_em")
 
 
+def cls_step_grads_fp64(g, args):
+    """Encoder gradients of the recorded CLS step evaluated in float64 by the oracle."""
+    dd = torch.float64
+    p = {k: v.to(dd).requires_grad_(True) for k, v in params_from(g, "enc0.").items()}
+    fus = [{k: v.to(dd) for k, v in params_from(g, "cls0.fuse%d." % i).items()} for i in (1, 2)]
+    mp = {k: v.to(dd) for k, v in params_from(g, "cls0.classifier.").items()}
+    r = od.disgat_traverse(p, fus, t(g["x"]).to(dd), t(g["indices"]), args.nhead, args.att, args.gnn_type,
+                           residue=args.residue, residue_type=args.residue_type)
+    tr = t(g["cls_idx_train"])
+    torch.nn.functional.nll_loss(od.mlp(mp, r["feats"][-1], cls=True)[tr], t(g["labels"])[tr]).backward()
+    return {k: v.grad for k, v in p.items()}
+
+
 @pytest.mark.parametrize("tag", MODEL_TAGS)
 def test_model_cls_step_grads_vs_reference_golden(tag):
     """First recorded train step (CLS, dropout 0): loss and encoder / fuser gradients."""
@@ -166,10 +180,12 @@ def test_model_cls_step_grads_vs_reference_golden(tag):
     assert_close(loss.item(), g["cls.log.loss_train"], RT, "loss_train")
     loss.backward()
     checked = 0
+    floor = group_floor([v for k, v in g.items() if k.startswith("cls.encgrad.")])
+    truth = cls_step_grads_fp64(g, args)
     for name, prm in enc.named_parameters():
         key = "cls.encgrad." + name
         if key in g:
-            assert_close(prm.grad.cpu(), g[key], RT_GRAD, key)
+            assert_close(prm.grad.cpu(), g[key], grad_tol(g[key], truth[name]), key, floor)
             checked += 1
     assert checked >= 8
     for name, prm in fus[0].named_parameters():
@@ -177,13 +193,21 @@ def test_model_cls_step_grads_vs_reference_golden(tag):
 
 
 # ------------------------------------------------------------------ fused channels vs CPU oracle
-def oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux):
+def grad_tol(ref32, ref64):
+    """Gradient tolerance: 2e-5, or 4x the error the reference's own fp32 arithmetic makes
+    against a float64 evaluation of the same formula (cancellation-dominated sums)."""
+    from helpers import rel_err
+    return max(RT_GRAD, 4.0 * rel_err(ref32, ref64))
+
+
+def oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux, dtype=torch.float32):
     """Run the oracle per channel; returns outputs and grads in the fused layout."""
     p = {}
     for c, l in enumerate(chs):
         for name, prm in l.named_parameters():
-            p["c%d.%s" % (c, name)] = prm.detach().cpu().clone().requires_grad_(True)
-    x = x_cpu.clone().requires_grad_(True)
+            p["c%d.%s" % (c, name)] = prm.detach().cpu().clone().to(dtype).requires_grad_(True)
+    x = x_cpu.clone().to(dtype).requires_grad_(True)
+    r_out, r_e, r_aux = r_out.to(dtype), r_e.to(dtype), [r.to(dtype) for r in r_aux]
     outs, es, auxs = [], [], []
     for c in range(len(chs)):
         o, e, au = od.disga_layer(p, "c%d." % c, x, idx, att, gnn, aux=aux)
@@ -227,6 +251,7 @@ def test_fused_channels_vs_oracle(case, att, gnn):
     r_out, r_e = torch.randn(n, C * D), torch.randn(e_cnt, C)
     r_aux = [torch.randn(a_.shape[1], C) for a_ in aux]
     o_ref, e_ref, au_ref, gx_ref, p_ref = oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux)
+    _, _, _, gx_64, p_64 = oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux, torch.float64)
 
     for l in chs:
         l.to(DEV).eval()
@@ -239,14 +264,16 @@ def test_fused_channels_vs_oracle(case, att, gnn):
         assert_close(au[k].cpu(), au_ref[k], RT, "aux%d" % k)
     loss = (out * r_out.to(DEV)).sum() + (e * r_e.to(DEV)).sum() + sum((a_ * r.to(DEV)).sum() for a_, r in zip(au, r_aux))
     loss.backward()
-    assert_close(x.grad.cpu(), gx_ref, RT_GRAD, "gx")
+    assert_close(x.grad.cpu(), gx_ref, grad_tol(gx_ref, gx_64), "gx")
+    floor = group_floor([v.grad for v in p_ref.values() if v.grad is not None])
     for c, l in enumerate(chs):
         for name, prm in l.named_parameters():
-            ref = p_ref["c%d.%s" % (c, name)].grad
+            key = "c%d.%s" % (c, name)
+            ref = p_ref[key].grad
             if ref is None:
                 assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
             else:
-                assert_close(prm.grad.cpu(), ref, RT_GRAD, "c%d.%s" % (c, name))
+                assert_close(prm.grad.cpu(), ref, grad_tol(ref, p_64[key].grad), key, floor)
 
 
 def test_isolated_rows_and_empty_pairs():
