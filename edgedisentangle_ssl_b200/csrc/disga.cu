@@ -381,8 +381,11 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
                 for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
                   if (ATT == 3) {
                     // dP accumulates U = sum_j de_ij lrelu'(z_ijd); scaled by a once per row
-                    const bool pos = pr[r] + q[u][r] > 0.0f;
-                    dP[r] += pos ? d : d001;
+                    const float z = pr[r] + q[u][r];
+                    const bool pos = z > 0.0f;
+                    const float w = pos ? d : d001;
+                    dP[r] += w;
+                    da[r] = fmaf(w, z, da[r]);      // de * lrelu(z) = de * lrelu'(z) * z
                     if (pos) mask |= 1u << r;
                   } else {
                     dP[r] = fmaf(d, q[u][r], dP[r]);
@@ -401,12 +404,8 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
       }
     }
     if (ATT == 3) {
-      // lrelu(z) = lrelu'(z) z  =>  da_d = sum_i P_i[d] U_i[d] + sum_j Q_j[d] U'_j[d]: per ROW, not per edge
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        da[r] = fmaf(pr[r], dP[r], da[r]);
-        dP[r] *= ar[r];
-      }
+      for (int r = 0; r < R; ++r) dP[r] *= ar[r];
     }
     if (it.slot < 0) {
       if (ATT >= 2) T::store(A.gP + srow * A.ldgp + off, dP, lane, A.D);
@@ -432,20 +431,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int CD = A.C * A.D;
-  float da[R];
-  zero<T>(da);
-  int da_grp = -1;
   for (; unit < A.n_units; unit += nwarps) {
     const int64_t item_id = unit / A.G;
     const int grp = static_cast<int>(unit - item_id * A.G);
     const Item it = A.items[item_id];
     const int c0 = grp * CPW;
     const int off = c0 * A.D;
-    if (ATT == 3 && grp != da_grp) {
-      if (da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
-      zero<T>(da);
-      da_grp = grp;
-    }
     int cidx[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
@@ -499,14 +490,10 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       }
     }
     if (ATT == 3) {
-      float qr[R], ar[R];
-      T::load(qr, A.Q + static_cast<int64_t>(it.row) * A.ldq + off, lane, A.D);
+      float ar[R];
       T::load(ar, A.a + off, lane, A.D);
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        da[r] = fmaf(qr[r], accQ[r], da[r]);   // source half of da (see the dst pass)
-        accQ[r] *= ar[r];
-      }
+      for (int r = 0; r < R; ++r) accQ[r] *= ar[r];
     }
     if (it.slot < 0) {
       if (HASV) T::store(A.gV + static_cast<int64_t>(it.row) * A.ldgv + off, accV, lane, A.D);
@@ -525,7 +512,6 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       }
     }
   }
-  if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
 }
 
 // SAGE: gX_j = sum_i sum_c alpha_drop_ij^c gh_i^c.  One warp per source-row chunk, all channels.

@@ -117,8 +117,6 @@ int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d,
  *                  element of P_i + Q_j (leaky-relu is piecewise linear, so the src pass needs
  *                  only lrelu'(z): 64 B/edge instead of gathering P_i, 2 KB/edge at C*D=512);
  *                  gh[N,C*Dv] scratch node tensor (grad wrt pre-activation)
- *   ga             uses lrelu(z) = lrelu'(z) z: da = sum_i P_i*U_i + sum_j Q_j*U'_j, accumulated per
- *                  ROW (U = dP / a), so there is no per-edge work for it
  * workspace >= edis_graph_workspace_bytes(g, 2*C*max(D,Dv) + 2*C). */
 int edis_disga_bwd(const edis_graph* g, const edis_layer_desc* d,
                    const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,

@@ -194,10 +194,10 @@ def test_model_cls_step_grads_vs_reference_golden(tag):
 
 # ------------------------------------------------------------------ fused channels vs CPU oracle
 def grad_tol(ref32, ref64):
-    """Gradient tolerance: 2e-5, or 4x the error the reference's own fp32 arithmetic makes
+    """Gradient tolerance: 2e-5, or 8x the error the reference's own fp32 arithmetic makes
     against a float64 evaluation of the same formula (cancellation-dominated sums)."""
     from helpers import rel_err
-    return max(RT_GRAD, 4.0 * rel_err(ref32, ref64))
+    return max(RT_GRAD, 8.0 * rel_err(ref32, ref64))
 
 
 def oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux, dtype=torch.float32):
