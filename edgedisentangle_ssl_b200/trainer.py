@@ -1,0 +1,342 @@
+"""Trainers on the B200 path (mirrors /root/reference/trainer.py:35-320 and
+pretrainer.py:372-857 for the DISGAT route).
+
+Same class names, constructor arguments, methods (`get_label_all`, `sample_train`, `train_step`,
+`inference`, `test`) and `log_info` keys as the reference.  What changed underneath:
+  * no dense N x N anywhere: SSL labels are edge lists taken from the CSR graph, pairs come from
+    the streaming bit-exact sampler (sampler.py);
+  * pair scoring, `stack+sum+sigmoid+adj_mse_loss` and DifHead's `cat + log_softmax + NLL` run as
+    fused libedis kernels (functional.PairScore / SslWmse / NllConstLabel);
+  * SupEdge / DisEdge skip the layer-2 aggregation and only score the channels they consume.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+import torch.optim as optim
+
+from . import functional as Fn
+from . import utils
+from .graph import as_graph
+from .layers import FuseLayer
+from .models import MLP
+from .sampler import homo_hetero_split, sample_pairs
+
+
+def fuse_feature(feature_list, fuse="last"):
+    """trainer.py:15-24."""
+    if fuse == "last":
+        return feature_list[-1]
+    if fuse == "avg":
+        return torch.mean(torch.stack(feature_list))
+    return torch.cat(feature_list, dim=-1)
+
+
+def cal_feat_dim(args):
+    """trainer.py:26-32."""
+    return args.nhid * args.enc_layer if args.fuse == "concat" else args.nhid
+
+
+def roc_f(output, labels):
+    """utils.Roc_F (utils.py:258-284): sklearn macro AUC / F1 on host copies (forces a sync)."""
+    from sklearn.metrics import f1_score, roc_auc_score
+    y = labels.detach().cpu()
+    prob = F.softmax(output, dim=-1).detach().cpu()
+    if labels.max() > 1:
+        auc = roc_auc_score(y, prob, average="macro", multi_class="ovr")
+    else:
+        auc = roc_auc_score(y, prob[:, 1], average="macro")
+    return auc, f1_score(y, torch.argmax(output, dim=-1).detach().cpu(), average="macro")
+
+
+class Trainer(object):
+    """Per-trainer fusers + one Adam per sub-model (trainer.py:35-60)."""
+
+    def __init__(self, args, model, weight):
+        assert args.model == "DISGAT", "the B200 path covers --model=DISGAT"
+        self.args = args
+        self.in_dim = cal_feat_dim(args)
+        self.loss_weight = weight
+        self.models = [model]
+        if args.residue:
+            self.fuse1 = FuseLayer(args, args.nhead, nfeat=args.nhid, residue=args.size)
+            self.fuse2 = FuseLayer(args, args.nhead, nfeat=args.nhid, residue=args.nhid)
+        else:
+            self.fuse1 = FuseLayer(args, args.nhead, nfeat=args.nhid)
+            self.fuse2 = FuseLayer(args, args.nhead, nfeat=args.nhid)
+        if args.cuda:
+            self.fuse1.cuda()
+            self.fuse2.cuda()
+        self.models += [self.fuse1, self.fuse2]
+        self.models_opt = [optim.Adam(m.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+                           for m in self.models]
+
+    @property
+    def fusers(self):
+        return [self.fuse1, self.fuse2]
+
+    def _begin_step(self):
+        for m, opt in zip(self.models, self.models_opt):
+            m.train()
+            opt.zero_grad()
+
+    def _finish_step(self, loss, always_step=False):
+        (loss * self.loss_weight).backward()
+        if always_step or self.loss_weight != 0:
+            for opt in self.models_opt:
+                opt.step()
+
+    def get_em(self, feature, adj):
+        return fuse_feature(self.models[0].get_em(feature, adj, self.fusers), fuse=self.args.fuse)
+
+    def reg_fuser(self):
+        """L1 norm of the fuser weights (trainer.py:136-142)."""
+        l1 = sum(p.abs().sum() for p in self.fuse1.parameters()) + sum(p.abs().sum() for p in self.fuse2.parameters())
+        return self.args.reg_weight * l1
+
+
+# --------------------------------------------------------------------------- downstream: CLS
+class ClsTrainer(Trainer):
+    """Node classification (trainer.py:150-320)."""
+
+    def __init__(self, args, model, labels, weight=1.0):
+        super().__init__(args, model, weight)
+        self.classifier = MLP(in_feat=self.in_dim, hidden_size=args.nhid, out_size=labels.max().item() + 1,
+                              layers=args.cls_layer)
+        if args.cuda:
+            self.classifier.cuda()
+        self.classifier_opt = optim.Adam(self.classifier.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+        self.models.append(self.classifier)
+        self.models_opt.append(self.classifier_opt)
+        self.idx_train, self.idx_val, self.idx_test, self.class_num_mat = utils.split(
+            labels.cpu(), train_ratio=args.node_sup_ratio)
+        if args.cuda:
+            self.idx_train, self.idx_val, self.idx_test = (t.cuda() for t in (self.idx_train, self.idx_val, self.idx_test))
+        self.host_metrics = True   # sklearn AUC / macro-F1 every step like trainer.py:210 (host sync)
+
+    def train_step(self, data, labels, epoch):
+        self._begin_step()
+        feature, adj = data
+        output = self.classifier(self.get_em(feature, adj), cls=True)
+        loss_log = F.nll_loss(output[self.idx_train], labels[self.idx_train])
+        acc_train = utils.accuracy(output[self.idx_train], labels[self.idx_train])
+        reg_log = self.reg_fuser()
+        loss_train = loss_log + reg_log if self.args.reg else loss_log
+        self._finish_step(loss_train, always_step=True)
+        with torch.no_grad():
+            loss_val = F.nll_loss(output[self.idx_val], labels[self.idx_val])
+            acc_val = utils.accuracy(output[self.idx_val], labels[self.idx_val])
+        log_info = {"loss_train": loss_log.item(), "acc_train": acc_train.item(), "loss_reg": reg_log.item(),
+                    "loss_val": loss_val.item(), "acc_val": acc_val.item()}
+        if self.host_metrics:
+            log_info["roc_val"], log_info["macroF_val"] = roc_f(output[self.idx_val], labels[self.idx_val])
+        print("Epoch: {:05d}".format(epoch + 1), "loss_train: {:.4f}".format(log_info["loss_train"]),
+              "loss_reg: {:.4f}".format(log_info["loss_reg"]), "acc_train: {:.4f}".format(log_info["acc_train"]),
+              "loss_val: {:.4f}".format(log_info["loss_val"]), "acc_val: {:.4f}".format(log_info["acc_val"]))
+        return log_info
+
+    def test(self, data, labels, epoch=0):
+        for m in self.models:
+            m.eval()
+        feature, adj = data
+        with torch.no_grad():
+            output = self.classifier(self.get_em(feature, adj), cls=True)
+            loss_test = F.nll_loss(output[self.idx_test], labels[self.idx_test])
+            acc_test = utils.accuracy(output[self.idx_test], labels[self.idx_test])
+        print("Test set results:", "loss= {:.4f}".format(loss_test.item()), "accuracy= {:.4f}".format(acc_test.item()))
+        roc_test, macro_f = roc_f(output[self.idx_test], labels[self.idx_test])
+        return {"loss_test": loss_test.item(), "acc_test": acc_test.item(), "roc_test": roc_test,
+                "macroF_test": macro_f}
+
+
+# --------------------------------------------------------------------------- SSL: edge labels
+class EdgeLabels:
+    """SSL supervision as edge lists (replaces the dense N x N label matrices of
+    pretrainer.py:440-456 / 667-680).  sets[k] = [2, E_k] int64 host array, row-major sorted."""
+
+    def __init__(self, n, sets):
+        self.n = n
+        self.sets = [np.ascontiguousarray(s, dtype=np.int64) for s in sets]
+
+
+def _edge_indices_host(adj):
+    g = as_graph(adj)
+    ex = g.export()
+    row = np.repeat(np.arange(g.n, dtype=np.int64), np.diff(ex["rowptr"]))
+    return g.n, np.stack([row, ex["col"].astype(np.int64)])
+
+
+class _PairTrainer(Trainer):
+    """Shared machinery of SupEdge / DisEdge: sample pairs, score them, fused weighted MSE."""
+
+    log_key = ""
+    banner = ""
+
+    def __init__(self, args, model, weight):
+        super().__init__(args, model, weight)
+        assert args.sparse, "the B200 path implements the sparse branch (--sparse)"
+        self.sparse = True
+        self.constrain_layer = args.constrain_layer
+        self.labels_ssl = None
+
+    def _ranges(self, nsets):
+        raise NotImplementedError
+
+    def sample_train(self, label=None):
+        """-> (adj_labels: list of [M_k] float32 device tensors, adj_masks: list of [2, M_k] int64)."""
+        lab = label if isinstance(label, EdgeLabels) else self.labels_ssl
+        dev = next(self.models[0].parameters()).device
+        labels, masks = [], []
+        for pos in lab.sets:
+            pairs, y = sample_pairs(lab.n, pos)
+            masks.append(torch.from_numpy(pairs).to(dev))
+            labels.append(torch.from_numpy(y).to(dev))
+        return labels, masks
+
+    def inference(self, data, sparse_edge_index=None):
+        feature, adj = data
+        return self.models[0].predict_adjs_sparse(feature, adj, self.fusers, auxiliary_edges=sparse_edge_index)
+
+    def _loss(self, data, labels, masks):
+        feature, adj = data
+        nsets = len(masks)
+        ranges = self._ranges(nsets)
+        r = self.models[0].traverse(feature, adj, self.fusers, aux=masks, aux_ranges=ranges,
+                                    need_layer2_agg=False)
+        n_pos = [int((y != 0).sum()) for y in labels]
+        loss = None
+        for layer, auxs in enumerate(r["aux"]):
+            if self.constrain_layer == 0 or self.constrain_layer == layer:
+                for k in range(nsets):
+                    term = Fn.SslWmse.apply(auxs[k], labels[k], n_pos[k])
+                    loss = term if loss is None else loss + term
+        if loss is None:
+            raise ValueError("--constrain_layer=%d selects no layer (it is compared with the 0-based layer "
+                             "index, pretrainer.py:728): use 0 (all) or 1 (second layer)" % self.constrain_layer)
+        return loss
+
+    def _train(self, data, label):
+        self._begin_step()
+        labels, masks = self.sample_train(label)
+        loss = self._loss(data, labels, masks)
+        self._finish_step(loss)
+        print(self.banner.format(loss.item()))
+        return {self.log_key: loss.item()}
+
+
+class SupEdgeTrainer(_PairTrainer):
+    """Edge-recovery SSL over all channels (pretrainer.py:657-776)."""
+
+    log_key = "loss_heads_sup"
+    banner = "Sup on heads loss : {}"
+
+    def get_label_all(self, feature, adj):
+        n, idx = _edge_indices_host(adj)
+        self.labels_ssl = EdgeLabels(n, [idx])
+        return self.labels_ssl
+
+    def sample_train(self, adj=None):
+        labels, masks = super().sample_train(adj)
+        return labels[0], masks
+
+    def _ranges(self, nsets):
+        return [(0, self.args.nhead)]
+
+    def train_step(self, data, gt_adj=None):
+        self._begin_step()
+        label, masks = self.sample_train(gt_adj)
+        loss = self._loss(data, [label], masks)
+        self._finish_step(loss)
+        print(self.banner.format(loss.item()))
+        return {self.log_key: loss.item()}
+
+
+class GeneratedEdgeTrainer(_PairTrainer):
+    """DisEdge: first C//2 channels recover same-label edges, the rest different-label edges
+    (pretrainer.py:372-654, dis_type 1)."""
+
+    log_key = "loss_head_disen"
+    banner = "Dis sup on edge loss : {}"
+
+    def __init__(self, args, model, weight):
+        super().__init__(args, model, weight)
+        self.dis_type = args.dis_type
+        assert self.dis_type == 1, "currently only use homo&hetero edge disentanglement"
+        if args.conformT:
+            raise NotImplementedError("--conformT (pretrainer.py:466-506) is listed under 'next' in SURVEY 8(f)")
+
+    def get_label_all(self, feature, adj, labels, load=True):
+        n, idx = _edge_indices_host(adj)
+        homo, het = homo_hetero_split(idx, labels.cpu().numpy())
+        for i, s in enumerate((homo, het)):
+            print("edge group {} for edge disentanglement SSL size: {}".format(i, float(s.shape[1])))
+        self.labels_ssl = EdgeLabels(n, [homo, het])
+        self.dis_adjs = self.labels_ssl
+        return self.labels_ssl
+
+    def _ranges(self, nsets):
+        c = self.args.nhead
+        return [(0, int(c / 2)), (int(c / 2), c)]
+
+    def train_step(self, data, pre_adjs=None):
+        return self._train(data, self.labels_ssl)
+
+
+# --------------------------------------------------------------------------- SSL: head diversity
+class DifHeadTrainer(Trainer):
+    """Which channel produced this node embedding?  (pretrainer.py:778-857).  The reference feeds
+    cat(x_in, elu(h'_c)) to a 2-layer MLP per channel; here the first Linear is split into its
+    x_in part (computed once) and its h' part (one GEMM over all channels), and the
+    log_softmax + NLL with the constant label c is one fused kernel per channel."""
+
+    def __init__(self, args, model, weight):
+        super().__init__(args, model, weight)
+        self.classifier1 = MLP(in_feat=args.nhid + args.size, hidden_size=args.nhid, out_size=args.nhead,
+                               layers=args.cls_layer)
+        self.classifier2 = MLP(in_feat=args.nhid * 2, hidden_size=args.nhid, out_size=args.nhead,
+                               layers=args.cls_layer)
+        if args.cuda:
+            self.classifier1.cuda()
+            self.classifier2.cuda()
+        self.classifier_opt1 = optim.Adam(self.classifier1.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+        self.classifier_opt2 = optim.Adam(self.classifier2.parameters(), lr=args.lr, weight_decay=args.weight_decay)
+        self.models += [self.classifier1, self.classifier2]
+        self.models_opt += [self.classifier_opt1, self.classifier_opt2]
+        self.nhead = args.nhead
+
+    def get_label_all(self, feature, adj):
+        return None
+
+    def inference(self, data):
+        feature, adj = data
+        return self.models[0].get_edge_em(feature, adj, self.fusers)
+
+    def _head_logits(self, clf, x_in, out):
+        """MLP(cat(x_in, out_c)) for every channel c without materialising the cat: [N, C, K]."""
+        n, fin = x_in.shape
+        c = self.nhead
+        d = out.shape[1] // c
+        mods = list(clf.model)
+        if len(mods) != 3:      # --cls_layer != 2: fall back to the literal formulation
+            cat = torch.cat([x_in.unsqueeze(1).expand(n, c, fin), out.reshape(n, c, d)], -1)
+            return clf.model(cat.reshape(n * c, fin + d)).reshape(n, c, -1)
+        lin0, act, lin1 = mods
+        z = F.linear(x_in, lin0.weight[:, :fin], lin0.bias).unsqueeze(1) \
+            + F.linear(out.reshape(n * c, d), lin0.weight[:, fin:]).reshape(n, c, -1)
+        return lin1(act(z))
+
+    def train_step(self, data, pre_dif=None):
+        self._begin_step()
+        feature, adj = data
+        r = self.models[0].traverse(feature, adj, self.fusers)
+        loss = None
+        for layer, clf in enumerate((self.classifier1, self.classifier2)):
+            logits = self._head_logits(clf, r["x_in"][layer], r["out"][layer])      # [N, C, K]
+            for c in range(self.nhead):
+                term = Fn.NllConstLabel.apply(logits[:, c, :], c)
+                loss = term if loss is None else loss + term
+        self._finish_step(loss)
+        print("diversity on heads loss : {}".format(loss.item()))
+        return {"loss_head_diversity": loss.item()}
+
+
+SSL_TRAINERS = {"DisEdge": GeneratedEdgeTrainer, "SupEdge": SupEdgeTrainer, "DifHead": DifHeadTrainer}

@@ -1,0 +1,140 @@
+"""GPU parity of the trainers' `train_step`s against the reference's recorded steps.
+
+tests/golden/model_*.npz hold, for four DISGAT configurations, one CLS, SupEdge, DisEdge and
+DifHead `train_step` run by the UNMODIFIED reference (dropout 0 so train mode is deterministic;
+RNG seeded right before each step): logged losses, encoder gradients after each step and the
+encoder after the four Adam updates.  This replays them on the B200 path -- sampler (CPU RNG
+order), fused pair scoring / loss kernels, DifHead tail, per-trainer Adam states.
+"""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+import edgedisentangle_ssl_b200 as edis
+from edgedisentangle_ssl_b200 import trainer as T
+from edgedisentangle_ssl_b200.utils import get_parser
+from helpers import load, t, assert_close, params_from, group_floor
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+MODEL_TAGS = ["model_a3_AT", "model_a1_SAGE", "model_a2_GCN", "model_a3_AT_res"]
+
+
+def seed_all(s):
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+def load_into(module, g, prefix):
+    module.load_state_dict({k: v.to(DEV) for k, v in params_from(g, prefix).items()}, strict=True)
+
+
+@pytest.mark.parametrize("tag", MODEL_TAGS)
+def test_train_steps_vs_reference_golden(tag):
+    g = load(tag)
+    args = get_parser().parse_args([str(a) for a in g["argv"]])
+    args.cuda, args.hetero, args.edge_num = True, True, 1
+    args.size = g["x"].shape[1]
+    x, labels = t(g["x"]).to(DEV), t(g["labels"]).to(DEV)
+    args.nclass = int(labels.max()) + 1
+    n = int(g["n"])
+    idx = torch.as_tensor(g["indices"])
+    adj = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).to(DEV)
+
+    seed_all(4)
+    enc = edis.DISGAT(args, nfeat=args.size, nhid=args.nhid, nclass=args.nhid, nheads=args.nhead,
+                      dropout=args.dropout).to(DEV)
+    sup = T.SupEdgeTrainer(args, enc, 1.0)
+    sup_lab = sup.get_label_all(x, adj)
+    dis = T.GeneratedEdgeTrainer(args, enc, 1.0)
+    dis_lab = dis.get_label_all(x, adj, labels)
+    dif = T.DifHeadTrainer(args, enc, 1.0)
+    cls = T.ClsTrainer(args, enc, labels, 1.0)
+    # same initial state as the recorded run (constructors above only fixed shapes / optimisers)
+    load_into(enc, g, "enc0.")
+    for nm, tr in (("sup", sup), ("dis", dis), ("dif", dif), ("cls", cls)):
+        load_into(tr.fuse1, g, nm + "0.fuse1.")
+        load_into(tr.fuse2, g, nm + "0.fuse2.")
+    load_into(dif.classifier1, g, "dif0.classifier1.")
+    load_into(dif.classifier2, g, "dif0.classifier2.")
+    load_into(cls.classifier, g, "cls0.classifier.")
+    cls.idx_train, cls.idx_val, cls.idx_test = (t(g["cls_idx_" + k]).to(DEV) for k in ("train", "val", "test"))
+    # the split itself replays utils.split's python-RNG order
+    assert int(g["cls_idx_train"].shape[0]) == int(cls.idx_train.shape[0])
+
+    def check(nm, log, rt_loss=1e-5, rt_grad=5e-5):
+        for k, v in log.items():
+            key = "%s.log.%s" % (nm, k)
+            if key in g and k.startswith("loss"):
+                assert_close(v, g[key], rt_loss, key)
+            elif key in g:
+                assert abs(v - float(g[key])) < 1e-6, (key, v, float(g[key]))
+        refs = {k[len(nm) + 9:]: v for k, v in g.items() if k.startswith(nm + ".encgrad.")}
+        floor = group_floor(refs.values())
+        seen = 0
+        for name, prm in enc.named_parameters():
+            if name in refs:
+                assert prm.grad is not None, name
+                assert_close(prm.grad.cpu(), refs[name], rt_grad, "%s grad %s" % (nm, name), floor)
+                seen += 1
+        assert seen == len(refs) and seen > 0
+        return log
+
+    seed_all(7)
+    check("cls", cls.train_step([x, adj], labels, 0))
+    seed_all(8)
+    check("sup", sup.train_step([x, adj], sup_lab))
+    seed_all(9)
+    check("dis", dis.train_step([x, adj], dis_lab))
+    seed_all(10)
+    check("dif", dif.train_step([x, adj], None))
+    for name, prm in dif.classifier1.named_parameters():
+        assert_close(prm.grad.cpu(), g["dif.cls1grad." + name], 5e-5, "dif classifier1 " + name)
+    # encoder after four Adam updates (one Adam state per trainer, like the reference)
+    final = enc.state_dict()
+    for k, v in params_from(g, "enc_final.").items():
+        assert_close(final[k].cpu(), v, 2e-4, "enc_final." + k)
+
+
+def test_sample_train_matches_reference_sets():
+    """Trainer-level sampler: pairs and labels bit-exact vs the reference's sample_train."""
+    g = load("model_a3_AT")
+    args = get_parser().parse_args([str(a) for a in g["argv"]])
+    args.cuda, args.hetero, args.size = True, True, g["x"].shape[1]
+    n = int(g["n"])
+    idx = torch.as_tensor(g["indices"])
+    adj = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).to(DEV)
+    enc = edis.DISGAT(args, nfeat=args.size, nhid=args.nhid, nclass=args.nhid, nheads=args.nhead, dropout=0.0).to(DEV)
+    sup = T.SupEdgeTrainer(args, enc, 1.0)
+    lab = sup.get_label_all(None, adj)
+    seed_all(8)
+    y, masks = sup.sample_train(lab)
+    assert np.array_equal(masks[0].cpu().numpy(), g["sup.sample_idx"])
+    assert np.array_equal(y.cpu().numpy(), g["sup.sample_lab"])
+    dis = T.GeneratedEdgeTrainer(args, enc, 1.0)
+    dis.get_label_all(None, adj, t(g["labels"]))
+    seed_all(9)
+    ys, ms = dis.sample_train()
+    for k in range(2):
+        assert np.array_equal(ms[k].cpu().numpy(), g["dis.sample_idx%d" % k])
+        assert np.array_equal(ys[k].cpu().numpy(), g["dis.sample_lab%d" % k])
+
+
+def test_cli_epoch_on_cora():
+    """The CLI loop runs end to end on bundled cora with the example script's flags
+    (Example_cora_full.sh:38, 2 epochs) and trains (loss decreases, finite)."""
+    import os
+    from edgedisentangle_ssl_b200.main import run
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+    hist = run(["--seed=4", "--model=DISGAT", "--used_edge=1", "--finetune", "--downstream=CLS", "--down_weight=1.0",
+                "--steps=5", "--nhead=4", "--dataset=cora", "--pretrain", "SupEdge", "DisEdge", "DifHead",
+                "--pre_weight", "1", "1", "1", "--pre_edge", "1", "1", "1", "--sparse", "--att=3",
+                "--constrain_layer=0", "--epochs=3", "--gnn_type=AT"], data_root=root)
+    assert len(hist) == 3
+    for h in hist:
+        for k in ("loss_train", "loss_heads_sup", "loss_head_disen", "loss_head_diversity"):
+            assert np.isfinite(h[k]), (k, h[k])
+    assert hist[-1]["loss_train"] < hist[0]["loss_train"]
