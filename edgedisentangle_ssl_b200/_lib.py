@@ -49,6 +49,7 @@ SIGNATURES = {
     "edis_version": (c_char_p, []),
     "edis_build_adjacency_host": (c_int64, [c_int64, c_int64, _i64p, _i64p, _f64p, _i64p, _i64p, _f32p]),
     "edis_graph_create": (c_int, [c_int64, c_int64, _i64p, _i64p, c_int, c_int, POINTER(c_void_p)]),
+    "edis_graph_create_rect": (c_int, [c_int64, c_int64, c_int64, _i64p, _i64p, c_int, c_int, POINTER(c_void_p)]),
     "edis_graph_destroy": (None, [c_void_p]),
     "edis_graph_info": (c_int, [c_void_p, _i64p]),
     "edis_graph_export": (c_int, [c_void_p, _i64p, _i32p, _i64p, _i64p, _i32p, _i32p]),

@@ -47,7 +47,7 @@ struct Schedule {
 }  // namespace edis
 
 struct edis_graph {
-  int64_t n = 0, e = 0, e_in = 0;
+  int64_t n = 0, n_cols = 0, e = 0, e_in = 0;   // n = destination rows, n_cols = source columns
   int device = 0;
   int sm_count = 148;
   int64_t max_in = 0, max_out = 0;

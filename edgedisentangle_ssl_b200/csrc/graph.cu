@@ -171,14 +171,19 @@ extern "C" int64_t edis_build_adjacency_host(int64_t n, int64_t m, const int64_t
 // ---------------------------------------------------------------------------------------
 extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, const int64_t* col,
                                  int max_chunk, int device, edis_graph** out) {
-  EDIS_CHECK_ARG(out && n > 0 && e_in >= 0 && (e_in == 0 || (row && col)),
-                 "edis_graph_create: bad arguments");
-  EDIS_CHECK_ARG(e_in < (int64_t(1) << 31) - 64 && n < (int64_t(1) << 31) - 64,
+  return edis_graph_create_rect(n, n, e_in, row, col, max_chunk, device, out);
+}
+
+extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, const int64_t* row,
+                                      const int64_t* col, int max_chunk, int device, edis_graph** out) {
+  EDIS_CHECK_ARG(out && n > 0 && n_cols >= n && e_in >= 0 && (e_in == 0 || (row && col)),
+                 "edis_graph_create: bad arguments (need n_cols >= n_rows > 0)");
+  EDIS_CHECK_ARG(e_in < (int64_t(1) << 31) - 64 && n_cols < (int64_t(1) << 31) - 64,
                  "edis_graph_create: n and e must fit int32");
   if (max_chunk <= 0) max_chunk = 256;
   bool sorted = true;
   for (int64_t k = 0; k < e_in; ++k) {
-    if (row[k] < 0 || row[k] >= n || col[k] < 0 || col[k] >= n) {
+    if (row[k] < 0 || row[k] >= n || col[k] < 0 || col[k] >= n_cols) {
       set_error("edis_graph_create: entry %lld out of range", (long long)k);
       return EDIS_ERR_ARG;
     }
@@ -186,6 +191,7 @@ extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, co
   }
   edis_graph* g = new edis_graph();
   g->n = n;
+  g->n_cols = n_cols;
   g->e_in = e_in;
   g->device = device;
   g->was_sorted = sorted;
@@ -198,7 +204,7 @@ extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, co
   } else {
     // stable (col, then row) counting sorts + coalesce duplicates (adj.coalesce(), layers.py:344)
     std::vector<int64_t> o1(e_in), o2(e_in), cnt;
-    counting_order(n, e_in, col, nullptr, o1.data(), cnt);
+    counting_order(n_cols, e_in, col, nullptr, o1.data(), cnt);
     counting_order(n, e_in, row, o1.data(), o2.data(), cnt);
     srow.reserve(e_in);
     scol.reserve(e_in);
@@ -215,7 +221,7 @@ extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, co
   g->e = e;
   g->h_rowptr = new int64_t[n + 1]();
   g->h_col = new int32_t[std::max<int64_t>(e, 1)];
-  g->h_cscptr = new int64_t[n + 1]();
+  g->h_cscptr = new int64_t[n_cols + 1]();
   g->h_cscrow = new int32_t[std::max<int64_t>(e, 1)];
   g->h_csceid = new int32_t[std::max<int64_t>(e, 1)];
   for (int64_t k = 0; k < e; ++k) {
@@ -225,12 +231,14 @@ extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, co
   }
   for (int64_t i = 0; i < n; ++i) {
     g->max_in = std::max(g->max_in, g->h_rowptr[i + 1]);
-    g->max_out = std::max(g->max_out, g->h_cscptr[i + 1]);
     g->h_rowptr[i + 1] += g->h_rowptr[i];
+  }
+  for (int64_t i = 0; i < n_cols; ++i) {
+    g->max_out = std::max(g->max_out, g->h_cscptr[i + 1]);
     g->h_cscptr[i + 1] += g->h_cscptr[i];
   }
   {
-    std::vector<int64_t> cur(g->h_cscptr, g->h_cscptr + n);
+    std::vector<int64_t> cur(g->h_cscptr, g->h_cscptr + n_cols);
     for (int64_t k = 0; k < e; ++k) {
       const int64_t pos = cur[scol[k]]++;
       g->h_cscrow[pos] = static_cast<int32_t>(srow[k]);
@@ -255,12 +263,12 @@ extern "C" int edis_graph_create(int64_t n, int64_t e_in, const int64_t* row, co
   g->dst = build_schedule_host(n, g->h_rowptr, max_chunk, items, split);
   if ((rc = upload(&g->dst.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->dst.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
-  g->src = build_schedule_host(n, g->h_cscptr, max_chunk, items, split);
+  g->src = build_schedule_host(n_cols, g->h_cscptr, max_chunk, items, split);
   if ((rc = upload(&g->src.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->src.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->rowptr, g->h_rowptr, n + 1)) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->col, g->h_col, e)) != EDIS_OK) return fail(rc);
-  if ((rc = upload(&g->cscptr, g->h_cscptr, n + 1)) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->cscptr, g->h_cscptr, n_cols + 1)) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->cscrow, g->h_cscrow, e)) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->csceid, g->h_csceid, e)) != EDIS_OK) return fail(rc);
   cudaSetDevice(prev_dev);
@@ -277,12 +285,13 @@ extern "C" void edis_graph_destroy(edis_graph* g) {
   delete g;
 }
 
-extern "C" int edis_graph_info(const edis_graph* g, int64_t info[9]) {
+extern "C" int edis_graph_info(const edis_graph* g, int64_t info[10]) {
   EDIS_CHECK_ARG(g && info, "edis_graph_info: null argument");
   info[0] = g->n; info[1] = g->e;
   info[2] = g->dst.n_items; info[3] = g->dst.n_slots;
   info[4] = g->src.n_items; info[5] = g->src.n_slots;
   info[6] = g->max_in; info[7] = g->max_out; info[8] = g->was_sorted ? 1 : 0;
+  info[9] = g->n_cols;
   return EDIS_OK;
 }
 
@@ -292,7 +301,7 @@ extern "C" int edis_graph_export(const edis_graph* g, int64_t* rowptr, int32_t* 
   if (rowptr) memcpy(rowptr, g->h_rowptr, (g->n + 1) * sizeof(int64_t));
   if (col) memcpy(col, g->h_col, g->e * sizeof(int32_t));
   if (perm) memcpy(perm, g->h_perm, g->e_in * sizeof(int64_t));  // sized by the INPUT entry count
-  if (cscptr) memcpy(cscptr, g->h_cscptr, (g->n + 1) * sizeof(int64_t));
+  if (cscptr) memcpy(cscptr, g->h_cscptr, (g->n_cols + 1) * sizeof(int64_t));
   if (cscrow) memcpy(cscrow, g->h_cscrow, g->e * sizeof(int32_t));
   if (csceid) memcpy(csceid, g->h_csceid, g->e * sizeof(int32_t));
   return EDIS_OK;

@@ -114,6 +114,8 @@ class DisGAFused(torch.autograd.Function):
         a = a.contiguous() if a is not None else None
         bias = bias.contiguous() if bias is not None else None
         n, e = graph.n, graph.e
+        if proj.shape[0] != graph.n_cols:
+            raise _lib.EdisError("projection has %d rows, graph has %d source nodes" % (proj.shape[0], graph.n_cols))
         out = torch.empty(n, CD, dtype=torch.float32, device=proj.device)
         hpre = torch.empty_like(out)
         edge_e = torch.empty(e, C, dtype=torch.float32, device=proj.device)
@@ -136,7 +138,8 @@ class DisGAFused(torch.autograd.Function):
         graph, d = ctx.graph, ctx.d
         C, D, att = d.C, d.D, d.att
         CD = C * D
-        n, e = graph.n, graph.e
+        n, e, nc = graph.n, graph.e, graph.n_cols
+        rect = nc > n          # destination-range partition: rows >= n are halo sources only
         off_p, off_q, off_v = ctx.offs
         ld, W, dev = proj.stride(0), proj.shape[1], proj.device
         if g_out is None:
@@ -147,18 +150,19 @@ class DisGAFused(torch.autograd.Function):
         g_sd = g_ss = gq_sep = None
         if att == 1:
             # the score columns of proj get their gradient through sdst/ssrc in torch
-            g_proj = torch.zeros(n, W, dtype=torch.float32, device=dev)
-            g_sd = torch.empty(n, C, dtype=torch.float32, device=dev)
-            g_ss = torch.empty(n, C, dtype=torch.float32, device=dev)
+            g_proj = torch.zeros(nc, W, dtype=torch.float32, device=dev)
+            g_sd = (torch.zeros if rect else torch.empty)(nc, C, dtype=torch.float32, device=dev)
+            g_ss = torch.empty(nc, C, dtype=torch.float32, device=dev)
             P, Q, ldp, ldq = _ptr(sdst), _ptr(ssrc), C, C
             gP, gQ, ldgp, ldgq = _ptr(g_sd), _ptr(g_ss), C, C
         else:
             covered = CD * (3 if att == 3 else 2)
-            g_proj = (torch.empty if W == covered else torch.zeros)(n, W, dtype=torch.float32, device=dev)
+            g_proj = (torch.empty if W == covered and not rect else torch.zeros)(nc, W, dtype=torch.float32,
+                                                                                 device=dev)
             P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
             gP, ldgp = _off(g_proj, off_p), W
             if off_q == off_p:      # att 2: P and Q are the same columns; sum the two grads
-                gq_sep = torch.empty(n, CD, dtype=torch.float32, device=dev)
+                gq_sep = torch.empty(nc, CD, dtype=torch.float32, device=dev)
                 gQ, ldgq = _ptr(gq_sep), CD
             else:
                 gQ, ldgq = _off(g_proj, off_q), W
@@ -195,6 +199,8 @@ class SageFused(torch.autograd.Function):
         X, ldx = _rows(X, "X")
         a = a.contiguous() if a is not None else None
         n, e, Fin = graph.n, graph.e, X.shape[1]
+        if X.shape[0] != graph.n_cols:
+            raise _lib.EdisError("X has %d rows, graph has %d source nodes" % (X.shape[0], graph.n_cols))
         neigh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
         edge_e = torch.empty(e, C, dtype=torch.float32, device=X.device)
         stats = torch.empty(n, 2 * C, dtype=torch.float32, device=X.device)
@@ -223,9 +229,10 @@ class SageFused(torch.autograd.Function):
         if g_edge_e is not None:
             g_edge_e = g_edge_e.contiguous()
         wdt = C if att == 1 else C * D
-        gP = torch.empty(n, wdt, dtype=torch.float32, device=X.device)
-        gQ = torch.empty(n, wdt, dtype=torch.float32, device=X.device)
-        gX = torch.empty(n, Fin, dtype=torch.float32, device=X.device)
+        nc = graph.n_cols
+        gP = (torch.zeros if nc > n else torch.empty)(nc, wdt, dtype=torch.float32, device=X.device)
+        gQ = torch.empty(nc, wdt, dtype=torch.float32, device=X.device)
+        gX = torch.empty(nc, Fin, dtype=torch.float32, device=X.device)
         ga = torch.zeros(C, D, dtype=torch.float32, device=X.device) if att == 3 else None
         edge_rec = _edge_rec(graph, d, X.device)
         gh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)

@@ -40,7 +40,9 @@ def build_adjacency(n, rows, cols, vals=None):
 class Graph:
     """Device-resident CSR + CSC + work schedules of one adjacency (edis_graph)."""
 
-    def __init__(self, n, row, col, device=None, max_chunk=0):
+    def __init__(self, n, row, col, device=None, max_chunk=0, n_cols=None):
+        """n destination rows; n_cols >= n source columns (rectangular = one rank's slice of a
+        destination-range partition, own nodes first then halo; default square)."""
         if device is None:
             device = torch.device("cuda", torch.cuda.current_device())
         device = torch.device(device)
@@ -52,13 +54,14 @@ class Graph:
         col = np.ascontiguousarray(col, dtype=np.int64)
         self._e_in = row.shape[0]
         h = c_void_p()
-        check(lib.edis_graph_create(n, row.shape[0], np_ptr(row, c_int64), np_ptr(col, c_int64),
-                                    int(max_chunk), self.device.index, ctypes.byref(h)), "edis_graph_create")
+        check(lib.edis_graph_create_rect(n, n if n_cols is None else int(n_cols), row.shape[0],
+                                         np_ptr(row, c_int64), np_ptr(col, c_int64), int(max_chunk),
+                                         self.device.index, ctypes.byref(h)), "edis_graph_create_rect")
         self._h = h
-        info = np.zeros(9, dtype=np.int64)
+        info = np.zeros(10, dtype=np.int64)
         check(lib.edis_graph_info(self._h, np_ptr(info, c_int64)), "edis_graph_info")
-        self.n, self.e = int(info[0]), int(info[1])
-        self.info = dict(n=self.n, e=self.e, dst_items=int(info[2]), dst_slots=int(info[3]),
+        self.n, self.e, self.n_cols = int(info[0]), int(info[1]), int(info[9])
+        self.info = dict(n=self.n, n_cols=self.n_cols, e=self.e, dst_items=int(info[2]), dst_slots=int(info[3]),
                          src_items=int(info[4]), src_slots=int(info[5]), max_in=int(info[6]),
                          max_out=int(info[7]), was_sorted=bool(info[8]))
         self._indices = None
@@ -81,7 +84,7 @@ class Graph:
         rowptr = np.empty(self.n + 1, dtype=np.int64)
         col = np.empty(max(self.e, 1), dtype=np.int32)
         perm = np.empty(max(self._e_in, 1), dtype=np.int64)
-        cscptr = np.empty(self.n + 1, dtype=np.int64)
+        cscptr = np.empty(self.n_cols + 1, dtype=np.int64)
         cscrow = np.empty(max(self.e, 1), dtype=np.int32)
         csceid = np.empty(max(self.e, 1), dtype=np.int32)
         check(lib.edis_graph_export(self._h, np_ptr(rowptr, c_int64), np_ptr(col, c_int32),

@@ -118,7 +118,7 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
     if gnn == "SAGE":
         neigh, edge_e = SageFused.apply(graph, att, C, D, P, Q, a, x, training, p, seed)   # [N, C*F]
         wp = torch.stack([l.ag_layer.proj.weight for l in chs], 0)                         # [C, D, 2F]
-        self_part = torch.einsum("nf,cdf->ncd", x, wp[:, :, :Fin])
+        self_part = torch.einsum("nf,cdf->ncd", x[:graph.n], wp[:, :, :Fin])
         neigh_part = torch.einsum("ncf,cdf->ncd", neigh.reshape(-1, C, Fin), wp[:, :, Fin:])
         h = self_part + neigh_part
         if l0.ag_layer.proj.bias is not None:

@@ -60,14 +60,22 @@ int64_t edis_build_adjacency_host(int64_t n, int64_t m, const int64_t* rows, con
 typedef struct edis_graph edis_graph;
 int edis_graph_create(int64_t n, int64_t e, const int64_t* row, const int64_t* col, int max_chunk,
                       int device, edis_graph** out);
+/* Rectangular variant for a destination-range partition of a larger graph (multi-GPU): rows
+ * are the n_rows destination nodes this rank owns, columns the n_cols >= n_rows source nodes it
+ * reads (its own nodes FIRST, then halo nodes), so destination node i is also source node i.
+ * Destination-side node tensors (out, hpre, g_out, gh, the P rows used) have n_rows rows,
+ * source-side ones (Q, V, gQ, gV) n_cols rows. */
+int edis_graph_create_rect(int64_t n_rows, int64_t n_cols, int64_t e, const int64_t* row,
+                           const int64_t* col, int max_chunk, int device, edis_graph** out);
 void edis_graph_destroy(edis_graph* g);
 
 /* info[0]=n, [1]=e, [2]=dst items, [3]=dst partial slots, [4]=src items, [5]=src partial slots,
- * [6]=max in-degree, [7]=max out-degree, [8]=1 if the input was already sorted (perm = identity) */
-int edis_graph_info(const edis_graph* g, int64_t info[9]);
+ * [6]=max in-degree, [7]=max out-degree, [8]=1 if the input was already sorted (perm = identity),
+ * [9]=n_cols */
+int edis_graph_info(const edis_graph* g, int64_t info[10]);
 /* copies of the structure arrays to HOST buffers (any may be NULL): rowptr[n+1], col[e],
  * perm[e_in] (input entry k -> CSR slot perm[k]; sized by the INPUT entry count, duplicates
- * map to the same slot), cscptr[n+1], cscrow[e], csceid[e] */
+ * map to the same slot), cscptr[n_cols+1], cscrow[e], csceid[e] */
 int edis_graph_export(const edis_graph* g, int64_t* rowptr, int32_t* col, int64_t* perm,
                       int64_t* cscptr, int32_t* cscrow, int32_t* csceid);
 /* bytes of scratch the layer ops need for a node tensor of `width` floats per row */
