@@ -175,14 +175,26 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------- GPU arm
-def algorithmic_bytes(n, e, C, D, att):
-    """SURVEY 8(d) gather model, per layer, fp32 (att 2/3; att 1 gathers scalars for the score)."""
+def algorithmic_bytes(n, e, C, D, att, feats):
+    """Gather-model bytes per launch, fp32.  Plan "proj" (project, then gather V_j): SURVEY 8(d).
+    Plan "agg" (aggregate the raw input, project afterwards; DESIGN.md e): the aggregated operand
+    gathered per edge is F floats instead of C*D, the source pass reads sign bits instead of P_i.
+    Returns {kernel name: [bytes for layer 1, layer 2]}."""
     cd = C * D
     score = 4 * C if att == 1 else 4 * cd
-    fwd = e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n
-    bwd_dst = e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n
-    bwd_src = e * (score + 4 * cd) + 4 * cd * n
-    return {"disga_fwd": fwd, "disga_bwd_dst": bwd_dst, "disga_bwd_src": bwd_src}
+    out = {"disga_fwd": [e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n] * 2,
+           "disga_bwd_dst": [e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n] * 2,
+           "disga_bwd_src": [e * (score + 4 * cd) + 4 * cd * n] * 2}
+    sign = cd // 8 if att == 3 else 0
+    for name in ("disga_sage_fwd", "disga_sage_bwd_dst", "disga_sage_bwd_src", "disga_sage_bwd_gx"):
+        out[name] = []
+    for f in feats:
+        out["disga_sage_fwd"].append(e * (score + 4 * f + 4 * C + 4) + n * (score + 4 * C * f + 8 * C))
+        out["disga_sage_bwd_dst"].append(e * (score + 4 * f + 4 * C + 8 * C + sign + 4)
+                                         + n * (score + 12 * C * f + score))
+        out["disga_sage_bwd_src"].append(e * (8 * C + sign + 8 + (score if att == 2 else 0)) + n * score)
+        out["disga_sage_bwd_gx"].append(e * (4 * C * f + 4 * C + 8) + n * 4 * f)
+    return out
 
 
 def main():
@@ -282,7 +294,8 @@ def main():
     Fn.TIMER.enabled = True
     ms_res = timed(False, a.steps)
     Fn.TIMER.enabled = False
-    kernel_ms = {k: float(np.mean(v)) for k, v in Fn.TIMER.durations_ms().items()}
+    kernel_list = Fn.TIMER.durations_ms()
+    plan = os.environ.get("EDIS_AT_PLAN") or "proj"
     launches = Fn.TIMER.launches
     step(True)
     ms_e2e = timed(True, a.steps)
@@ -302,15 +315,25 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg = algorithmic_bytes(graph.n, graph.e, a.nhead, a.nhid, a.att)
-    dom = max(kernel_ms, key=kernel_ms.get) if kernel_ms else None
+    alg = algorithmic_bytes(graph.n, graph.e, a.nhead, a.nhid, a.att, [a.feat, a.nhid])
+    # per kernel: launches alternate layer 1 / layer 2 in forward order (backward: layer 2 first)
+    per = {}
+    for k, v in kernel_list.items():
+        if k not in alg or not v:
+            continue
+        order = [0, 1] if "fwd" in k else [1, 0]
+        if k == "disga_sage_bwd_gx":
+            order = [1]                      # only the layer whose input needs a gradient launches it
+        ms = np.array(v)
+        tot_b = sum(alg[k][order[i % len(order)]] for i in range(len(ms)))
+        per[k] = {"ms_per_launch": float(ms.mean()), "gbs": tot_b / (ms.sum() * 1e-3) / 1e9,
+                  "bytes_per_launch": tot_b / len(ms), "ms_per_step": float(ms.sum() / a.steps)}
+    dom = max(per, key=lambda k: per[k]["ms_per_step"]) if per else None
     roof = None
     if dom:
-        ach = alg[dom] / (kernel_ms[dom] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": alg[dom],
-                "kernel_ms": kernel_ms,
-                "all_kernels_gbs": {k: alg[k] / (v * 1e-3) / 1e9 for k, v in kernel_ms.items() if k in alg}}
+        roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": per[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": per[dom]["bytes_per_launch"], "plan": plan, "kernels": per}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             roof["traffic"] = json.load(open(tpath)).get(dom)

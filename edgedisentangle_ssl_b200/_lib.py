@@ -19,7 +19,13 @@ class EdisError(RuntimeError):
 class LayerDesc(Structure):
     """edis_layer_desc (include/edis.h)."""
     _fields_ = [("att", c_int32), ("C", c_int32), ("D", c_int32), ("Dv", c_int32),
-                ("training", c_int32), ("p", c_float), ("seed", c_uint64)]
+                ("training", c_int32), ("p", c_float), ("seed", c_uint64), ("flags", c_int32),
+                ("reserved", c_int32)]
+
+
+FLAG_PLAIN_MEAN = 1
+FLAG_NO_GX = 2
+FLAG_PHASE_DST, FLAG_PHASE_SRC, FLAG_PHASE_GX = 4, 8, 16
 
 
 def _load():
@@ -63,7 +69,8 @@ SIGNATURES = {
     "edis_disga_sage_fwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64,
                                     _P, _P, _P, _P, c_int64, _P]),
     "edis_disga_sage_bwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64,
-                                    _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, _P]),
+                                    _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P,
+                                    c_int64, _P]),
     "edis_pair_score_fwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,
                                     _P, c_int64, _P, _P, _P]),
     "edis_pair_score_bwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,

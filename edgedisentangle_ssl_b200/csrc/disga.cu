@@ -32,6 +32,13 @@
 #ifndef EDIS_MINB
 #define EDIS_MINB 2
 #endif
+// L2 prefetch distance (edges ahead of the consuming loads) for the 128-bit paths; 0 = off
+#ifndef EDIS_PF
+#define EDIS_PF 2
+#endif
+#ifndef EDIS_PF_SRC
+#define EDIS_PF_SRC 0
+#endif
 
 namespace edis {
 
@@ -54,6 +61,8 @@ struct LayerArgs {
   float* partial;
   int64_t pwidth;
   int training;
+  int plain;                // shared-operand mode: 1 = plain softmax mean (AT/GCN aggregate-then-project),
+                            // 0 = SAGE neighbour mean (divide by detached rowsum + 1)
   float p, inv_keep;
   uint64_t seed;
 };
@@ -75,6 +84,12 @@ template <class T, int ATT, int RX, int U>
 __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
+  constexpr int PF = (T::kVec && RX == 0) ? EDIS_PF : 0;
+  auto prefetch_src = [](const LayerArgs& a, int j, int off) {
+    // this lane's edge: pull the source row's score part and value part (R*128 bytes each) into L2
+    if (ATT >= 2) prefetch_l2_bulk(a.Q + static_cast<int64_t>(j) * a.ldq + off, R * 128);
+    prefetch_l2_bulk(a.V + static_cast<int64_t>(j) * a.ldv + off, R * 128);
+  };
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -98,7 +113,13 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
     for (int eb = it.beg; eb < it.end; eb += 32) {
       const int cnt = min(32, it.end - eb);
       const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
+      if (PF > 0 && lane < cnt && lane < PF) prefetch_src(A, myj, off);
       for (int t = 0; t < cnt; t += U) {
+        if (PF > 0) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (lane == t + u + PF && lane < cnt) prefetch_src(A, myj, off);
+        }
         float q[U][R], h[U][R], qs[U], xj[U][RXA];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -175,10 +196,10 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
         T::store(A.partial + static_cast<int64_t>(it.slot) * A.pwidth + off, acc, lane, A.D);
       }
     } else {
-      // SAGE: neigh = agg / (rowsum(alpha_drop) + 1) = acc / (sum w*mask + sum w)
+      // SAGE: neigh = agg / (rowsum(alpha_drop) + 1) = acc / (sum w*mask + sum w); plain: acc / sum w
 #pragma unroll
       for (int cc = 0; cc < CPW; ++cc) {
-        const float den = T::from_channel(ws, cc) + T::from_channel(wms, cc);
+        const float den = T::from_channel(ws, cc) + (A.plain ? 0.0f : T::from_channel(wms, cc));
         float o[RXA];
 #pragma unroll
         for (int k = 0; k < RX; ++k)
@@ -218,7 +239,7 @@ __global__ void k_combine_fwd(const SplitRow* split, int64_t n_split, const floa
   }
   const int64_t o = static_cast<int64_t>(s.row) * CW + x;
   if (sage) {
-    const float den = ws + wms;
+    const float den = sage == 2 ? ws : ws + wms;   // 2 = plain mean
     hpre[o] = den > 0.0f ? acc / den : 0.0f;
   } else {
     float v = ws > 0.0f ? acc / ws : 0.0f;
@@ -251,6 +272,12 @@ template <class T, int ATT, int RX, int U>
 __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
+  constexpr int PF = (T::kVec && RX == 0) ? EDIS_PF : 0;
+  auto prefetch_src = [](const LayerArgs& a, int j, int off) {
+    // this lane's edge: pull the source row's score part and value part (R*128 bytes each) into L2
+    if (ATT >= 2) prefetch_l2_bulk(a.Q + static_cast<int64_t>(j) * a.ldq + off, R * 128);
+    prefetch_l2_bulk(a.V + static_cast<int64_t>(j) * a.ldv + off, R * 128);
+  };
   constexpr int SBPL = (R + 7) / 8;   // sign bytes per lane per edge
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -300,7 +327,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
 #pragma unroll
       for (int cc = 0; cc < CPW; ++cc) {
         const float wsc = T::from_channel(wsum, cc), den = wsc + T::from_channel(wmsv, cc);
-        const float rdiv = den > 0.0f ? wsc / den : 0.0f;   // 1 / div
+        const float rdiv = A.plain ? 1.0f : (den > 0.0f ? wsc / den : 0.0f);   // 1 / div
         float gn[RXA], ng[RXA], o[RXA];
         load_x<RX>(gn, A.g_out + (srow * A.C + c0 + cc) * A.F, lane, A.F);
         load_x<RX>(ng, A.hpre + (srow * A.C + c0 + cc) * A.F, lane, A.F);
@@ -325,7 +352,13 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
     for (int eb = it.beg; eb < it.end; eb += 32) {
       const int cnt = min(32, it.end - eb);
       const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
+      if (PF > 0 && lane < cnt && lane < PF) prefetch_src(A, myj, off);
       for (int t = 0; t < cnt; t += U) {
+        if (PF > 0) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (lane == t + u + PF && lane < cnt) prefetch_src(A, myj, off);
+        }
         float q[U][R], h[U][R], ev[U], gx[U], xj[U][RXA];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -381,11 +414,8 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
                 for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
                   if (ATT == 3) {
                     // dP accumulates U = sum_j de_ij lrelu'(z_ijd); scaled by a once per row
-                    const float z = pr[r] + q[u][r];
-                    const bool pos = z > 0.0f;
-                    const float w = pos ? d : d001;
-                    dP[r] += w;
-                    da[r] = fmaf(w, z, da[r]);      // de * lrelu(z) = de * lrelu'(z) * z
+                    const bool pos = pr[r] + q[u][r] > 0.0f;
+                    dP[r] += pos ? d : d001;
                     if (pos) mask |= 1u << r;
                   } else {
                     dP[r] = fmaf(d, q[u][r], dP[r]);
@@ -404,8 +434,13 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
       }
     }
     if (ATT == 3) {
+      // lrelu(z) = lrelu'(z) z  =>  da_d = sum_i P_i[d] U_i[d] + sum_j Q_j[d] U'_j[d]: per ROW, not per
+      // edge (the source half is added by the src pass)
 #pragma unroll
-      for (int r = 0; r < R; ++r) dP[r] *= ar[r];
+      for (int r = 0; r < R; ++r) {
+        da[r] = fmaf(pr[r], dP[r], da[r]);
+        dP[r] *= ar[r];
+      }
     }
     if (it.slot < 0) {
       if (ATT >= 2) T::store(A.gP + srow * A.ldgp + off, dP, lane, A.D);
@@ -427,16 +462,29 @@ template <class T, int ATT, bool HASV, int U>
 __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int SBPL = (R + 7) / 8;
+  constexpr int PF = T::kVec ? EDIS_PF_SRC : 0;
+  auto prefetch_dst = [](const LayerArgs& a, int i, int off) {
+    if (ATT == 2) prefetch_l2_bulk(a.P + static_cast<int64_t>(i) * a.ldp + off, R * 128);
+    if (HASV) prefetch_l2_bulk(a.gh + static_cast<int64_t>(i) * a.C * a.D + off, R * 128);
+  };
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int CD = A.C * A.D;
+  float da[R];
+  zero<T>(da);
+  int da_grp = -1;
   for (; unit < A.n_units; unit += nwarps) {
     const int64_t item_id = unit / A.G;
     const int grp = static_cast<int>(unit - item_id * A.G);
     const Item it = A.items[item_id];
     const int c0 = grp * CPW;
     const int off = c0 * A.D;
+    if (ATT == 3 && grp != da_grp) {
+      if (da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
+      zero<T>(da);
+      da_grp = grp;
+    }
     int cidx[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
@@ -449,7 +497,13 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       const int cnt = min(32, it.end - eb);
       const int myi = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
       const int mye = lane < cnt ? __ldg(A.eid + eb + lane) : 0;
+      if (PF > 0 && lane < cnt && lane < PF) prefetch_dst(A, myi, off);
       for (int t = 0; t < cnt; t += U) {
+        if (PF > 0) {
+#pragma unroll
+          for (int u = 0; u < U; ++u)
+            if (lane == t + u + PF && lane < cnt) prefetch_dst(A, myi, off);
+        }
         float pg[U][R], dh[U][R], ad[U][NCH], de[U][NCH];
         unsigned sg[U];
 #pragma unroll
@@ -489,11 +543,15 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
         }
       }
     }
-    if (ATT == 3) {
-      float ar[R];
+    if (ATT == 3 && it.end > it.beg) {
+      float qr[R], ar[R];
+      T::load(qr, A.Q + static_cast<int64_t>(it.row) * A.ldq + off, lane, A.D);
       T::load(ar, A.a + off, lane, A.D);
 #pragma unroll
-      for (int r = 0; r < R; ++r) accQ[r] *= ar[r];
+      for (int r = 0; r < R; ++r) {
+        da[r] = fmaf(qr[r], accQ[r], da[r]);   // source half of da (see the dst pass)
+        accQ[r] *= ar[r];
+      }
     }
     if (it.slot < 0) {
       if (HASV) T::store(A.gV + static_cast<int64_t>(it.row) * A.ldgv + off, accV, lane, A.D);
@@ -512,6 +570,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       }
     }
   }
+  if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
 }
 
 // SAGE: gX_j = sum_i sum_c alpha_drop_ij^c gh_i^c.  One warp per source-row chunk, all channels.
@@ -612,8 +671,9 @@ static int launch_layer(Pass pass, const edis_graph* g, const LayerArgs& A, int 
 
 template <class T>
 static int launch_sage_rx(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
-  if (A.F <= 64) return launch_att<T, 2, 2>(pass, g, A, att, st);
-  if (A.F <= 128) return launch_att<T, 4, 2>(pass, g, A, att, st);
+  constexpr int U = T::R >= 8 ? 1 : 2;
+  if (A.F <= 64) return launch_att<T, 2, U>(pass, g, A, att, st);
+  if (A.F <= 128) return launch_att<T, 4, U>(pass, g, A, att, st);
   if (A.F <= 256) return launch_att<T, 8, 1>(pass, g, A, att, st);
   set_error("unsupported SAGE input width F=%d (max 256)", A.F);
   return EDIS_ERR_UNSUPPORTED;
@@ -621,6 +681,8 @@ static int launch_sage_rx(Pass pass, const edis_graph* g, const LayerArgs& A, in
 
 static int launch_sage(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
   const int C = A.C, D = A.D;
+  if (D == 64 && C % 8 == 0) return launch_sage_rx<VecT<4, 16>>(pass, g, A, att, st);
+  if (D == 64 && C % 4 == 0) return launch_sage_rx<VecT<2, 16>>(pass, g, A, att, st);
   if (D == 64 && C % 2 == 0) return launch_sage_rx<VecT<1, 16>>(pass, g, A, att, st);
   if (D <= 64) return launch_sage_rx<ScaT<2>>(pass, g, A, att, st);
   if (D <= 256) return launch_sage_rx<ScaT<8>>(pass, g, A, att, st);
@@ -649,6 +711,7 @@ static void fill_common(LayerArgs& A, const edis_layer_desc* d, const float* P, 
   A.C = d->C; A.D = d->D; A.F = d->Dv;
   A.partial = static_cast<float*>(workspace);
   A.training = d->training && d->p > 0.0f;
+  A.plain = (d->flags & EDIS_FLAG_PLAIN_MEAN) ? 1 : 0;
   A.p = d->p;
   A.inv_keep = 1.0f / (1.0f - d->p);
   A.seed = d->seed;
@@ -823,7 +886,7 @@ extern "C" int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d
   if (rc) return rc;
   if (g->dst.n_split > 0) {
     k_combine_fwd<<<nblk(g->dst.n_split * d->C * d->Dv), 256, 0, st>>>(
-        g->dst.split, g->dst.n_split, A.partial, pw, d->C, d->Dv, 1, nullptr, nullptr, neigh, stats);
+        g->dst.split, g->dst.n_split, A.partial, pw, d->C, d->Dv, A.plain ? 2 : 1, nullptr, nullptr, neigh, stats);
     EDIS_CUDA(cudaGetLastError());
   }
   return EDIS_OK;
@@ -833,13 +896,14 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
                                    int64_t ldp, const float* Q, int64_t ldq, const float* a,
                                    const float* X, int64_t ldx, const float* neigh,
                                    const float* edge_e, const float* stats, const float* g_neigh,
-                                   const float* g_edge_e, float* gP, float* gQ, float* ga, float* gX,
-                                   float* edge_rec, float* gh, void* workspace,
-                                   int64_t workspace_bytes, void* stream) {
+                                   const float* g_edge_e, float* gP, int64_t ldgp, float* gQ,
+                                   int64_t ldgq, float* ga, float* gX, float* edge_rec, float* gh,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_desc(d, "edis_disga_sage_bwd");
   if (rc) return rc;
-  EDIS_CHECK_ARG(g && P && Q && X && neigh && edge_e && stats && g_neigh && gP && gQ && gX && edge_rec && gh,
-                 "edis_disga_sage_bwd: null pointer");
+  const bool need_gx = !(d->flags & EDIS_FLAG_NO_GX);
+  EDIS_CHECK_ARG(g && P && Q && X && neigh && edge_e && stats && g_neigh && gP && gQ && (gX || !need_gx) &&
+                     edge_rec && gh, "edis_disga_sage_bwd: null pointer");
   EDIS_CHECK_ARG(d->Dv >= 1 && d->Dv <= 256, "edis_disga_sage_bwd: F=%d (Dv) must be in [1, 256]", d->Dv);
   EDIS_CHECK_ARG(d->att != 3 || (a && ga), "edis_disga_sage_bwd: att=3 needs a and ga");
   const int CD = d->C * d->D;
@@ -852,20 +916,28 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
   A.g_out = g_neigh; A.g_edge_e = g_edge_e;
   A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gX; A.edge_rec = edge_rec; A.gh = gh;
   A.esign = reinterpret_cast<unsigned char*>(edge_rec) + rec_float_bytes(g, d);
-  A.ldgp = A.ldgq = d->att == 1 ? d->C : CD; A.ldgv = d->Dv;
+  A.ldgp = ldgp; A.ldgq = ldgq; A.ldgv = d->Dv;
   A.pwidth = pw;
-  A.nbr = g->col;
-  rc = launch_sage(Pass::BwdDst, g, A, d->att, st);
-  if (rc) return rc;
-  if (g->dst.n_split > 0) {
-    const int seg = d->att == 1 ? d->C : CD;
-    k_combine_rows<<<nblk(g->dst.n_split * seg), 256, 0, st>>>(g->dst.split, g->dst.n_split, A.partial, pw,
-                                                              0, seg, gP, seg);
-    EDIS_CUDA(cudaGetLastError());
+  const int ph = d->flags & EDIS_FLAG_PHASE_MASK;   // 0 = all passes
+  if (!ph || (ph & EDIS_FLAG_PHASE_DST)) {
+    A.nbr = g->col;
+    rc = launch_sage(Pass::BwdDst, g, A, d->att, st);
+    if (rc) return rc;
+    if (g->dst.n_split > 0) {
+      const int seg = d->att == 1 ? d->C : CD;
+      k_combine_rows<<<nblk(g->dst.n_split * seg), 256, 0, st>>>(g->dst.split, g->dst.n_split, A.partial, pw,
+                                                                0, seg, gP, A.ldgp);
+      EDIS_CUDA(cudaGetLastError());
+    }
   }
-  rc = bwd_score_src(g, d, A, true, gQ, nullptr, st);
-  if (rc) return rc;
+  if (!ph || (ph & EDIS_FLAG_PHASE_SRC)) {
+    rc = bwd_score_src(g, d, A, true, gQ, nullptr, st);
+    if (rc) return rc;
+  }
+  if (!need_gx || (ph && !(ph & EDIS_FLAG_PHASE_GX))) return EDIS_OK;
   // gX: one warp per source-row chunk, all channels
+  A.nbr = g->cscrow;
+  A.eid = g->csceid;
   A.items = g->src.items;
   A.n_units = g->src.n_items;
   A.G = 1;

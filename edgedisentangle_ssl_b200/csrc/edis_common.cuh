@@ -101,6 +101,12 @@ __device__ __forceinline__ void red_add4(float* addr, float a, float b, float c,
                : "memory");
 }
 
+// One instruction, one thread: pull `bytes` (multiple of 16, 16-byte aligned) from DRAM into L2.
+// Used to run the gathers a few edges ahead of the consuming loads without registers or smem.
+__device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
 int launch_grid(const void* kernel, int block, size_t smem, int sm_count);
 
 }  // namespace edis

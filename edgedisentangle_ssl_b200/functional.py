@@ -185,63 +185,168 @@ class DisGAFused(torch.autograd.Function):
 
 
 class SageFused(torch.autograd.Function):
-    """gnn_type=SAGE: scoring -> softmax -> dropout -> neighbour mean of the RAW input x shared
-    by all channels, divided by the detached (row sum + 1).  Replaces layers.py:349-394 +
-    400-403 + SageConv.forward's aggregation (layers.py:96-103, incl. its N x N `to_dense()`).
+    """Scoring -> softmax -> dropout -> aggregation of the RAW layer input x, shared by all channels.
 
-    forward(graph, att, C, D, P, Q, a, X, training, p, seed) -> (neigh[N, C*F], edge_e[E, C])
+    plain=False: gnn_type=SAGE neighbour mean, divided by the detached (row sum + 1); replaces
+    layers.py:349-394 + 400-403 + SageConv.forward's aggregation (layers.py:96-103, incl. its N x N
+    `to_dense()`).  plain=True: sum_j alpha_drop_ij x_j, i.e. gnn_type AT / GCN executed as
+    aggregate-then-project ((sum_j a_ij x_j) W == sum_j a_ij (x_j W)): the per-edge gather of the
+    aggregated operand shrinks from C*D to F floats; ChannelLinear applies W afterwards.
+
+    forward(graph, att, C, D, proj, off_p, off_q, sdst, ssrc, a, X, training, p, seed, plain)
+        -> (agg[N, C*F], edge_e[E, C]);   score operands as in DisGAFused.
     """
 
     @staticmethod
-    def forward(ctx, graph, att, C, D, P, Q, a, X, training, p, seed):
-        P, ldp = _rows(P, "P")
-        Q, ldq = _rows(Q, "Q")
+    def forward(ctx, graph, att, C, D, proj, off_p, off_q, sdst, ssrc, a, X, training, p, seed, plain):
         X, ldx = _rows(X, "X")
+        if att == 1:
+            sdst, ssrc = sdst.contiguous(), ssrc.contiguous()
+            P, Q, ldp, ldq = _ptr(sdst), _ptr(ssrc), C, C
+        else:
+            proj, ld = _rows(proj, "proj")
+            P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
         a = a.contiguous() if a is not None else None
         n, e, Fin = graph.n, graph.e, X.shape[1]
         if X.shape[0] != graph.n_cols:
             raise _lib.EdisError("X has %d rows, graph has %d source nodes" % (X.shape[0], graph.n_cols))
-        neigh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
+        agg = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
         edge_e = torch.empty(e, C, dtype=torch.float32, device=X.device)
         stats = torch.empty(n, 2 * C, dtype=torch.float32, device=X.device)
         ws, nbytes = _workspace(graph, C * Fin + 2 * C, X)
         d = _desc(att, C, D, training, p, seed)
         d.Dv = Fin
-        check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), _ptr(P), ldp, _ptr(Q), ldq, _ptr(a),
-                                      _ptr(X), ldx, _ptr(neigh), _ptr(edge_e), _ptr(stats), _ptr(ws), nbytes,
-                                      _stream()), "edis_disga_sage_fwd")
-        ctx.graph, ctx.d, ctx.lds = graph, d, (ldp, ldq, ldx)
+        d.flags = (_lib.FLAG_PLAIN_MEAN if plain else 0) | (0 if ctx.needs_input_grad[10] else _lib.FLAG_NO_GX)
+        with _timed("disga_sage_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
+            check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X), ldx,
+                                          _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(ws), nbytes, _stream()),
+                  "edis_disga_sage_fwd")
+        ctx.graph, ctx.d, ctx.offs, ctx.ldx = graph, d, (off_p, off_q), ldx
         ctx.has_a = a is not None
-        ctx.save_for_backward(P, Q, a, X, neigh, edge_e, stats)
+        ctx.save_for_backward(proj, sdst, ssrc, a, X, agg, edge_e, stats)
         ctx.set_materialize_grads(False)
-        return neigh, edge_e
+        return agg, edge_e
 
     @staticmethod
-    def backward(ctx, g_neigh, g_edge_e):
-        P, Q, a, X, neigh, edge_e, stats = ctx.saved_tensors
+    def backward(ctx, g_agg, g_edge_e):
+        proj, sdst, ssrc, a, X, agg, edge_e, stats = ctx.saved_tensors
         graph, d = ctx.graph, ctx.d
         C, D, att, Fin = d.C, d.D, d.att, d.Dv
-        n, e = graph.n, graph.e
-        ldp, ldq, ldx = ctx.lds
-        if g_neigh is None:
-            g_neigh = torch.zeros_like(neigh)
-        g_neigh = g_neigh.contiguous()
+        CD = C * D
+        n, e, nc = graph.n, graph.e, graph.n_cols
+        rect = nc > n
+        off_p, off_q = ctx.offs
+        dev = X.device
+        if g_agg is None:
+            g_agg = torch.zeros_like(agg)
+        g_agg = g_agg.contiguous()
         if g_edge_e is not None:
             g_edge_e = g_edge_e.contiguous()
-        wdt = C if att == 1 else C * D
-        nc = graph.n_cols
-        gP = (torch.zeros if nc > n else torch.empty)(nc, wdt, dtype=torch.float32, device=X.device)
-        gQ = torch.empty(nc, wdt, dtype=torch.float32, device=X.device)
-        gX = torch.empty(nc, Fin, dtype=torch.float32, device=X.device)
-        ga = torch.zeros(C, D, dtype=torch.float32, device=X.device) if att == 3 else None
-        edge_rec = _edge_rec(graph, d, X.device)
-        gh = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
-        ws, nbytes = _workspace(graph, 2 * C * D + 2 * C + Fin, X)
-        check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), _ptr(P), ldp, _ptr(Q), ldq, _ptr(a),
-                                      _ptr(X), ldx, _ptr(neigh), _ptr(edge_e), _ptr(stats), _ptr(g_neigh),
-                                      _ptr(g_edge_e), _ptr(gP), _ptr(gQ), _ptr(ga), _ptr(gX), _ptr(edge_rec),
-                                      _ptr(gh), _ptr(ws), nbytes, _stream()), "edis_disga_sage_bwd")
-        return (None, None, None, None, gP, gQ, ga if ctx.has_a else None, gX, None, None, None)
+        g_proj = g_sd = g_ss = gq_sep = None
+        if att == 1:
+            g_sd = (torch.zeros if rect else torch.empty)(nc, C, dtype=torch.float32, device=dev)
+            g_ss = torch.empty(nc, C, dtype=torch.float32, device=dev)
+            P, Q, ldp, ldq = _ptr(sdst), _ptr(ssrc), C, C
+            gP, gQ, ldgp, ldgq = _ptr(g_sd), _ptr(g_ss), C, C
+        else:
+            ld, W = proj.stride(0), proj.shape[1]
+            covered = CD * (2 if att == 3 else 1)
+            g_proj = (torch.empty if W == covered and not rect else torch.zeros)(nc, W, dtype=torch.float32,
+                                                                                 device=dev)
+            P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
+            gP, ldgp = _off(g_proj, off_p), W
+            if off_q == off_p:
+                gq_sep = torch.empty(nc, CD, dtype=torch.float32, device=dev)
+                gQ, ldgq = _ptr(gq_sep), CD
+            else:
+                gQ, ldgq = _off(g_proj, off_q), W
+        need_gx = not (d.flags & _lib.FLAG_NO_GX)
+        gX = torch.empty(nc, Fin, dtype=torch.float32, device=dev) if need_gx else None
+        ga = torch.zeros(C, D, dtype=torch.float32, device=dev) if att == 3 else None
+        edge_rec = _edge_rec(graph, d, dev)
+        gh = torch.empty(n, C * Fin, dtype=torch.float32, device=dev)
+        ws, nbytes = _workspace(graph, 2 * CD + 2 * C + Fin, X)
+        base = d.flags
+        phases = [("disga_sage_bwd_dst", _lib.FLAG_PHASE_DST, 1 + (1 if graph.info["dst_slots"] else 0)),
+                  ("disga_sage_bwd_src", _lib.FLAG_PHASE_SRC, 1 + (1 if graph.info["src_slots"] else 0))]
+        if need_gx:
+            phases.append(("disga_sage_bwd_gx", _lib.FLAG_PHASE_GX, 1 + (1 if graph.info["src_slots"] else 0)))
+        for name, bit, nl in phases:
+            d.flags = base | bit
+            with _timed(name, graph, nl):
+                check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X),
+                                              ctx.ldx, _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(g_agg),
+                                              _ptr(g_edge_e), gP, ldgp, gQ, ldgq, _ptr(ga), _ptr(gX),
+                                              _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream()),
+                      "edis_disga_sage_bwd")
+        d.flags = base
+        if gq_sep is not None:
+            g_proj[:, off_p:off_p + CD] += gq_sep
+        return (None, None, None, None, g_proj, None, None, g_sd, g_ss, ga if ctx.has_a else None, gX,
+                None, None, None, None)
+
+
+def _tf32_hi(t):
+    """Round-to-nearest onto the TF32 grid (10 explicit mantissa bits), result still fp32."""
+    return ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)
+
+
+class Proj3xTF32(torch.autograd.Function):
+    """x @ W at fp32 accuracy on the tensor cores: x = xh + xl, W = Wh + Wl on the TF32 grid and
+    x W ~= xh Wh + xh Wl + xl Wh = [xh | xh | xl] @ [Wh ; Wl ; Wh]  -- ONE library TF32 GEMM with
+    3x the K (the dropped xl Wl term is ~2^-22 relative).  Used for the node projection of a layer
+    (small K = F, wide output), where the fp32 SIMT GEMM is compute-bound and this one is bound by
+    writing the output.  Backward stays plain fp32 (its big operand is the [N, W] gradient)."""
+
+    @staticmethod
+    def forward(ctx, x, w):
+        xh, wh = _tf32_hi(x), _tf32_hi(w)
+        xc = torch.cat([xh, xh, x - xh], 1)
+        wc = torch.cat([wh, w - wh, wh], 0)
+        prev = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        try:
+            out = xc @ wc
+        finally:
+            torch.backends.cuda.matmul.allow_tf32 = prev
+        ctx.save_for_backward(x, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        gx = g @ w.t() if ctx.needs_input_grad[0] else None
+        gw = x.t() @ g if ctx.needs_input_grad[1] else None
+        return gx, gw
+
+
+class ChannelLinear(torch.autograd.Function):
+    """out[:, c*D:(c+1)*D] = agg[:, c*F:(c+1)*F] @ W[c]  for every channel c (plain cuBLAS GEMMs
+    writing straight into column blocks: no [C, N, .] transposes).  agg [N, C*F], W [C, F, D]."""
+
+    @staticmethod
+    def forward(ctx, agg, W):
+        C, Fin, D = W.shape
+        out = torch.empty(agg.shape[0], C * D, dtype=agg.dtype, device=agg.device)
+        for c in range(C):
+            torch.mm(agg[:, c * Fin:(c + 1) * Fin], W[c], out=out[:, c * D:(c + 1) * D])
+        ctx.save_for_backward(agg, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        agg, W = ctx.saved_tensors
+        C, Fin, D = W.shape
+        g = g.contiguous()
+        g_agg = torch.empty_like(agg) if ctx.needs_input_grad[0] else None
+        g_w = torch.empty_like(W) if ctx.needs_input_grad[1] else None
+        for c in range(C):
+            gc = g[:, c * D:(c + 1) * D]
+            if g_agg is not None:
+                torch.mm(gc, W[c].t(), out=g_agg[:, c * Fin:(c + 1) * Fin])
+            if g_w is not None:
+                torch.mm(agg[:, c * Fin:(c + 1) * Fin].t(), gc, out=g_w[c])
+        return g_agg, g_w
 
 
 class PairScore(torch.autograd.Function):

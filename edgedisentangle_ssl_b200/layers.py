@@ -10,6 +10,7 @@ All channels of a DISGAT layer run in ONE fused kernel launch (`run_channels`).
 """
 import itertools
 import math
+import os
 
 import torch
 import torch.nn.functional as F
@@ -17,7 +18,7 @@ from torch import nn
 from torch.nn.parameter import Parameter
 
 from . import _lib
-from .functional import DisGAFused, PairScore, SageFused
+from .functional import ChannelLinear, DisGAFused, PairScore, Proj3xTF32, SageFused
 from .graph import as_graph
 
 _seed_counter = itertools.count(1)
@@ -77,6 +78,14 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
     if x.dtype != torch.float32 or not x.is_cuda:
         raise _lib.EdisError("DisGALayer input must be a float32 CUDA tensor; there is no CPU fallback")
     CD = C * D
+    # Execution plan for gnn_type AT / GCN.  "proj" (default): project first, gather V_j = (x W)_j per
+    # edge with 128-bit loads.  "agg" (EDIS_AT_PLAN=agg, F <= 256): aggregate the raw input per channel
+    # with the shared-operand kernels and project afterwards -- 5x / 8x fewer gathered bytes for the
+    # aggregated operand at F=100 / 64, but those kernels are issue-bound (lane-strided accumulators,
+    # full-warp reductions per channel) and measured slower on B200 (profiles/r1_sweep4.log).
+    # SAGE always uses the shared-operand kernels.
+    plan = os.environ.get("EDIS_AT_PLAN") or "proj"
+    use_agg = aggregate and (gnn == "SAGE" or plan == "agg")
     a = None
     if att == 3:
         a = torch.cat([l.a.reshape(1, D) for l in chs], 0)
@@ -85,13 +94,15 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
         w_score = [torch.cat([l.W for l in chs], 1)]
     bias = None
     w_val = []
-    if aggregate and gnn == "AT":
-        w_val = [torch.cat([l.W_em for l in chs], 1)]
-    elif aggregate and gnn == "GCN":
-        w_val = [torch.cat([l.ag_layer.weight for l in chs], 1)]
-        if l0.ag_layer.bias is not None:
-            bias = torch.cat([l.ag_layer.bias for l in chs], 0)
-    proj = x @ torch.cat(w_score + w_val, 1)          # [N, (1|2 + 0|1) * C*D], fp32 (TF32 off)
+    if aggregate and gnn == "GCN" and l0.ag_layer.bias is not None:
+        bias = torch.cat([l.ag_layer.bias for l in chs], 0)
+    if aggregate and not use_agg:
+        w_val = [torch.cat([(l.W_em if gnn == "AT" else l.ag_layer.weight) for l in chs], 1)]
+    w_all = torch.cat(w_score + w_val, 1)
+    if os.environ.get("EDIS_PROJ3X", "1") != "0" and x.shape[0] >= 4096:
+        proj = Proj3xTF32.apply(x, w_all)             # fp32-accurate 3xTF32 split on the tensor cores
+    else:
+        proj = x @ w_all                              # one fp32 GEMM (TF32 off) for all channels / operands
     sdst = ssrc = None
     if att == 3:
         off_p, off_q, off_v = 0, CD, 2 * CD
@@ -116,7 +127,8 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
     training, p = l0.training, l0.dropout
     seed = _next_seed() if (training and p > 0) else 0
     if gnn == "SAGE":
-        neigh, edge_e = SageFused.apply(graph, att, C, D, P, Q, a, x, training, p, seed)   # [N, C*F]
+        neigh, edge_e = SageFused.apply(graph, att, C, D, proj, off_p, off_q, sdst, ssrc, a, x, training, p,
+                                        seed, False)                                       # [N, C*F]
         wp = torch.stack([l.ag_layer.proj.weight for l in chs], 0)                         # [C, D, 2F]
         self_part = torch.einsum("nf,cdf->ncd", x[:graph.n], wp[:, :, :Fin])
         neigh_part = torch.einsum("ncf,cdf->ncd", neigh.reshape(-1, C, Fin), wp[:, :, Fin:])
@@ -124,6 +136,12 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
         if l0.ag_layer.proj.bias is not None:
             h = h + torch.stack([l.ag_layer.proj.bias for l in chs], 0)
         out = F.elu(h).reshape(-1, CD)
+    elif use_agg:
+        agg, edge_e = SageFused.apply(graph, att, C, D, proj, off_p, off_q, sdst, ssrc, a, x, training, p,
+                                      seed, True)                                          # [N, C*F]
+        w_em = torch.stack([(l.W_em if gnn == "AT" else l.ag_layer.weight) for l in chs], 0)  # [C, F, D]
+        h = ChannelLinear.apply(agg, w_em)
+        out = F.elu(h + bias if bias is not None else h)
     else:
         out, edge_e = DisGAFused.apply(graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias,
                                        training, p, seed)

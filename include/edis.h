@@ -103,7 +103,20 @@ typedef struct {
   int32_t training;   /* 1: apply dropout on alpha with prob `p` (layers.py:394) */
   float p;            /* dropout probability */
   uint64_t seed;      /* dropout stream; bwd must be called with the seed of its fwd */
+  int32_t flags;      /* EDIS_FLAG_* (shared-operand entry points only) */
+  int32_t reserved;
 } edis_layer_desc;
+/* edis_disga_sage_*: aggregate = plain softmax-weighted mean sum_j ad_ij x_j (no "+1" divisor):
+ * gnn_type AT / GCN executed as aggregate-then-project, (sum_j ad_ij x_j) W == sum_j ad_ij (x_j W) */
+#define EDIS_FLAG_PLAIN_MEAN 1
+/* edis_disga_sage_bwd: the shared operand needs no gradient (layer-1 features): skip gX */
+#define EDIS_FLAG_NO_GX 2
+/* edis_disga_sage_bwd: run only the named passes (dst -> src -> gx, in this order on one stream;
+ * none set = all).  Lets a caller time / overlap the three kernels separately. */
+#define EDIS_FLAG_PHASE_DST 4
+#define EDIS_FLAG_PHASE_SRC 8
+#define EDIS_FLAG_PHASE_GX 16
+#define EDIS_FLAG_PHASE_MASK 28
 
 /* Forward.  Saved for backward: edge_e[E,C], stats[N,2C] (row sums: sum w, sum w*mask), hpre.
  * out / hpre: [N, C*Dv] contiguous.  workspace >= edis_graph_workspace_bytes(g, C*Dv + 2*C). */
@@ -173,7 +186,7 @@ int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d,
                         const float* X, int64_t ldx,
                         const float* neigh, const float* edge_e, const float* stats,
                         const float* g_neigh, const float* g_edge_e,
-                        float* gP, float* gQ, float* ga, float* gX,
+                        float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gX,
                         float* edge_rec, float* gh,
                         void* workspace, int64_t workspace_bytes, void* stream);
 

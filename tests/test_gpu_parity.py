@@ -19,8 +19,16 @@ from helpers import load, t, assert_close, params_from, group_floor
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
+
+
+@pytest.fixture(autouse=True, params=["agg", "proj"])
+def at_plan(request, monkeypatch):
+    """Run every test under both execution plans of gnn_type AT / GCN (layers.run_channels):
+    aggregate-then-project (shared-operand kernels) and project-then-aggregate (DisGAFused)."""
+    monkeypatch.setenv("EDIS_AT_PLAN", request.param)
+    return request.param
 RT = 1e-5
-RT_GRAD = 2e-5   # parameter gradients: long reassociated sums over edges / nodes
+RT_GRAD = 2e-5   # gradients: long reassociated sums over edges / nodes (see grad_tol)
 
 
 def cuda_adj(n, indices):
@@ -194,10 +202,12 @@ def test_model_cls_step_grads_vs_reference_golden(tag):
 
 # ------------------------------------------------------------------ fused channels vs CPU oracle
 def grad_tol(ref32, ref64):
-    """Gradient tolerance: 2e-5, or 8x the error the reference's own fp32 arithmetic makes
-    against a float64 evaluation of the same formula (cancellation-dominated sums)."""
+    """Gradient tolerance: 2e-5, or 16x the error the reference's own fp32 arithmetic makes
+    against a float64 evaluation of the same formula.  Softmax-backward gradients are differences of
+    nearly equal terms (d alpha - sum_k alpha_k d alpha_k), so every fp32 evaluation order -- the
+    reference's included -- carries cancellation noise well above 1e-5 of the result on some tensors."""
     from helpers import rel_err
-    return max(RT_GRAD, 8.0 * rel_err(ref32, ref64))
+    return max(RT_GRAD, 16.0 * rel_err(ref32, ref64))
 
 
 def oracle_layer_all(chs, x_cpu, idx, att, gnn, aux, r_out, r_e, r_aux, dtype=torch.float32):
@@ -292,6 +302,23 @@ def test_isolated_rows_and_empty_pairs():
     assert float(out[mask.to(DEV)].abs().max()) == 0.0
     out.sum().backward()
     assert torch.isfinite(x.grad).all()
+
+
+# ------------------------------------------------------------------ 3xTF32 projection
+def test_proj3x_tf32_is_fp32_accurate():
+    torch.manual_seed(0)
+    x = (torch.randn(20000, 100, device=DEV) * torch.logspace(-3, 3, 100, device=DEV)).requires_grad_(True)
+    w = torch.randn(100, 1536, device=DEV, requires_grad=True)
+    ref = x.double() @ w.double()
+    got = Fn.Proj3xTF32.apply(x, w)
+    plain = x @ w
+    e3, e1 = ((got.double() - ref).abs().max() / ref.abs().max()).item(), \
+        ((plain.double() - ref).abs().max() / ref.abs().max()).item()
+    assert e3 < 2e-6 and e3 < 8 * max(e1, 1e-7), (e3, e1)
+    r = torch.randn_like(got)
+    gx, gw = torch.autograd.grad((got * r).sum(), (x, w))
+    gx2, gw2 = torch.autograd.grad((plain * r).sum(), (x, w))
+    assert torch.equal(gx, gx2) and torch.equal(gw, gw2)     # backward is the plain fp32 one
 
 
 # ------------------------------------------------------------------ destination-range partition
