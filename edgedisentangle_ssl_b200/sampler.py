@@ -61,3 +61,36 @@ def sample_pairs(n, pos_indices, chunk_rows=None):
     check(m, "edis_merge_pairs_host")
     key = out_key[:m]
     return np.stack([key // n, key % n]), out_lab[:m].copy()
+
+
+def sample_pairs_device(n, pos_key, generator=None):
+    """Distribution-equivalent sampler for graphs where N x N uniforms are not an option
+    ('infeasible at N = 2.4 M').  Same law as `sample_pairs` -- an iid
+    Bernoulli(3*rho) mask over the N x N cells, united with a uniformly random third of the
+    positives -- but drawn in O(M): K ~ Binomial(N^2, 3*rho) (normal approximation), K distinct
+    cells uniformly at random (draw, dedup, top up), union, sort, label.  Not bit-exact with the
+    reference's RNG stream; runs entirely on the device of `pos_key` (sorted int64 keys i*n+j).
+    Returns (indices[2, M] int64, label[M] float32) on that device."""
+    dev = pos_key.device
+    e_l = pos_key.numel()
+    cells = float(n) * float(n)
+    thr = (torch.tensor(float(e_l), dtype=torch.float32) / (n * n)).item() * 3
+    mean, var = cells * thr, cells * thr * (1.0 - thr)
+    z = torch.randn((), generator=generator, device=dev).item() if generator is not None else torch.randn(()).item()
+    k = int(max(0, round(mean + (var ** 0.5) * z)))
+    key = torch.empty(0, dtype=torch.int64, device=dev)
+    need = k
+    while need > 0:
+        draw = int(need * 1.05) + 16
+        hi = torch.randint(0, n, (draw,), device=dev, generator=generator)
+        lo = torch.randint(0, n, (draw,), device=dev, generator=generator)
+        key = torch.unique(torch.cat([key, hi * n + lo]))
+        if key.numel() > k:        # drop a random surplus so that exactly k distinct cells remain
+            keep = torch.randperm(key.numel(), device=dev, generator=generator)[:k]
+            key = key[keep]
+        need = k - key.numel()
+    forced = pos_key[torch.randperm(e_l, device=dev, generator=generator)[: e_l // 3]]
+    key = torch.unique(torch.cat([key, forced]))
+    pos = torch.searchsorted(pos_key, key).clamp_(max=max(e_l - 1, 0))
+    label = (pos_key[pos] == key).to(torch.float32) if e_l else torch.zeros_like(key, dtype=torch.float32)
+    return torch.stack([torch.div(key, n, rounding_mode="floor"), key % n]), label

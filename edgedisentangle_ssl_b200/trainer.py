@@ -9,6 +9,8 @@ Same class names, constructor arguments, methods (`get_label_all`, `sample_train
     fused libedis kernels (functional.PairScore / SslWmse / NllConstLabel);
   * SupEdge / DisEdge skip the layer-2 aggregation and only score the channels they consume.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn.functional as F
@@ -19,7 +21,7 @@ from . import utils
 from .graph import as_graph
 from .layers import FuseLayer
 from .models import MLP
-from .sampler import homo_hetero_split, sample_pairs
+from .sampler import homo_hetero_split, sample_pairs, sample_pairs_device
 
 
 def fuse_feature(feature_list, fuse="last"):
@@ -111,7 +113,9 @@ class ClsTrainer(Trainer):
             labels.cpu(), train_ratio=args.node_sup_ratio)
         if args.cuda:
             self.idx_train, self.idx_val, self.idx_test = (t.cuda() for t in (self.idx_train, self.idx_val, self.idx_test))
-        self.host_metrics = True   # sklearn AUC / macro-F1 every step like trainer.py:210 (host sync)
+        # sklearn AUC / macro-F1 every step like trainer.py:210 (forces a device->host sync);
+        # EDIS_HOST_METRICS=0 drops them from train_step (they stay in test())
+        self.host_metrics = os.environ.get("EDIS_HOST_METRICS", "1") != "0"
 
     def train_step(self, data, labels, epoch):
         self._begin_step()
@@ -156,6 +160,13 @@ class EdgeLabels:
     def __init__(self, n, sets):
         self.n = n
         self.sets = [np.ascontiguousarray(s, dtype=np.int64) for s in sets]
+        self._keys = None
+
+    def keys_on(self, device):
+        """Sorted int64 keys i*n+j of every set, resident on `device` (for the device sampler)."""
+        if self._keys is None or self._keys[0].device != torch.device(device):
+            self._keys = [torch.from_numpy(s[0] * self.n + s[1]).to(device) for s in self.sets]
+        return self._keys
 
 
 def _edge_indices_host(adj):
@@ -186,10 +197,18 @@ class _PairTrainer(Trainer):
         lab = label if isinstance(label, EdgeLabels) else self.labels_ssl
         dev = next(self.models[0].parameters()).device
         labels, masks = [], []
-        for pos in lab.sets:
-            pairs, y = sample_pairs(lab.n, pos)
-            masks.append(torch.from_numpy(pairs).to(dev))
-            labels.append(torch.from_numpy(y).to(dev))
+        # "exact": the reference's RNG stream replayed bit for bit (O(N^2) uniforms on the host);
+        # "device": same distribution in O(M) on the GPU (needed beyond N ~ 5e4; EDIS_SAMPLER=device)
+        mode = os.environ.get("EDIS_SAMPLER") or ("exact" if lab.n <= 50_000 else "device")
+        for k, pos in enumerate(lab.sets):
+            if mode == "exact":
+                pairs, y = sample_pairs(lab.n, pos)
+                masks.append(torch.from_numpy(pairs).to(dev))
+                labels.append(torch.from_numpy(y).to(dev))
+            else:
+                pairs, y = sample_pairs_device(lab.n, lab.keys_on(dev)[k])
+                masks.append(pairs)
+                labels.append(y)
         return labels, masks
 
     def inference(self, data, sparse_edge_index=None):

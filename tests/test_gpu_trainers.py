@@ -143,3 +143,30 @@ def test_cli_epoch_on_cora():
         for k in ("loss_train", "loss_heads_sup", "loss_head_disen", "loss_head_diversity"):
             assert np.isfinite(h[k]), (k, h[k])
     assert hist[-1]["loss_train"] < hist[0]["loss_train"]
+
+
+def test_device_sampler_has_the_reference_distribution():
+    """O(M) device sampler vs the bit-exact one: same pair count (Binomial mean), same share of
+    positives, forced third of the positives present, sorted unique keys, exact labels."""
+    from edgedisentangle_ssl_b200.sampler import sample_pairs, sample_pairs_device
+    from oracle import graph as og
+    rng = np.random.RandomState(0)
+    n = 3000
+    idx, _ = og.build_adjacency(n, rng.randint(0, n, 20000), rng.randint(0, n, 20000))
+    seed_all(1)
+    exact = [sample_pairs(n, idx)[0].shape[1] for _ in range(3)]
+    pos_key = torch.from_numpy(idx[0] * n + idx[1]).to(DEV)
+    counts, pos_frac = [], []
+    for s in range(6):
+        gen = torch.Generator(device=DEV).manual_seed(s)
+        pairs, lab = sample_pairs_device(n, pos_key, gen)
+        key = pairs[0] * n + pairs[1]
+        assert torch.all(key[1:] > key[:-1])
+        assert torch.equal(lab.bool(), torch.isin(key, pos_key))
+        counts.append(pairs.shape[1])
+        pos_frac.append(lab.mean().item())
+        assert int(lab.sum()) >= idx.shape[1] // 3
+    e = idx.shape[1]
+    expect = 3 * e + e // 3          # Bernoulli hits + forced third (overlap is O(rho) small)
+    assert abs(np.mean(counts) - expect) < 0.02 * expect and abs(np.mean(exact) - expect) < 0.02 * expect
+    assert abs(np.mean(pos_frac) - (e // 3 + 3 * e * e / n / n) / expect) < 0.01
