@@ -45,9 +45,9 @@ _f64p = POINTER(c_double)
 _descp = POINTER(LayerDesc)
 _P = c_void_p  # device pointers travel as integers
 
-# (g, d, P, ldp, Q, ldq, a, V, ldv, bias, hpre, edge_e, stats, g_out, g_edge_e,
+# (g, d, P, ldp, Q, ldq, a, V, ldv, bias, hpre, edge_e, stats, esign, g_out, g_edge_e,
 #  gP, ldgp, gQ, ldgq, ga, gV, ldgv, edge_rec, gh, workspace, workspace_bytes, stream)
-_BWD_ARGS = [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P,
+_BWD_ARGS = [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, _P, _P, _P, _P, _P,
              _P, c_int64, _P, c_int64, _P, _P, c_int64, _P, _P, _P, c_int64, _P]
 
 SIGNATURES = {
@@ -61,15 +61,16 @@ SIGNATURES = {
     "edis_graph_export": (c_int, [c_void_p, _i64p, _i32p, _i64p, _i64p, _i32p, _i32p]),
     "edis_graph_workspace_bytes": (c_int64, [c_void_p, c_int64]),
     "edis_disga_fwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P,
-                               _P, _P, _P, _P, _P, c_int64, _P]),
+                               _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "edis_disga_rec_bytes": (c_int64, [c_void_p, _descp]),
+    "edis_disga_sign_bytes": (c_int64, [c_void_p, _descp]),
     "edis_disga_bwd": (c_int, _BWD_ARGS),
     "edis_disga_bwd_dst": (c_int, _BWD_ARGS),
     "edis_disga_bwd_src": (c_int, _BWD_ARGS),
     "edis_disga_sage_fwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64,
-                                    _P, _P, _P, _P, c_int64, _P]),
+                                    _P, _P, _P, _P, _P, c_int64, _P]),
     "edis_disga_sage_bwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64,
-                                    _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P,
+                                    _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P,
                                     c_int64, _P]),
     "edis_pair_score_fwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,
                                     _P, c_int64, _P, _P, _P]),

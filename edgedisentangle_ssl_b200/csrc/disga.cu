@@ -29,6 +29,10 @@
 #ifndef EDIS_U_KV4
 #define EDIS_U_KV4 1
 #endif
+// destination pass of att 3 (no Q gather): edges in flight on the whole-row path
+#ifndef EDIS_UB_KV4
+#define EDIS_UB_KV4 2
+#endif
 #ifndef EDIS_MINB
 #define EDIS_MINB 2
 #endif
@@ -56,10 +60,11 @@ struct LayerArgs {
   // backward
   const float *g_out, *g_edge_e;
   float *gP, *gQ, *ga, *gV, *edge_rec, *gh;
-  unsigned char* esign;              // att 3: sign bits of P_i + Q_j per edge (dst pass -> src pass)
+  unsigned char* esign;              // att 3: sign bits of P_i + Q_j per edge (forward -> both backward passes)
   int64_t ldgp, ldgq, ldgv;          // row strides of gP, gQ, gV
   float* partial;
   int64_t pwidth;
+  int hot_min;              // neighbours with heat >= hot_min get the evict_last L2 policy (4 = off)
   int training;
   int plain;                // shared-operand mode: 1 = plain softmax mean (AT/GCN aggregate-then-project),
                             // 0 = SAGE neighbour mean (divide by detached rowsum + 1)
@@ -85,10 +90,15 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
   constexpr int PF = (T::kVec && RX == 0) ? EDIS_PF : 0;
-  auto prefetch_src = [](const LayerArgs& a, int j, int off) {
+  constexpr int SBPL = (R + 7) / 8;   // sign bytes per lane per edge
+  const uint64_t pol_hot = A.hot_min <= 3 ? l2_policy_evict_last() : l2_policy_evict_normal();
+  const uint64_t pol_cold = A.hot_min <= 3 ? l2_policy_evict_first() : l2_policy_evict_normal();
+  auto prefetch_src = [&](const LayerArgs& a, int raw, int off) {
     // this lane's edge: pull the source row's score part and value part (R*128 bytes each) into L2
-    if (ATT >= 2) prefetch_l2_bulk(a.Q + static_cast<int64_t>(j) * a.ldq + off, R * 128);
-    prefetch_l2_bulk(a.V + static_cast<int64_t>(j) * a.ldv + off, R * 128);
+    const int64_t j = raw & kIdMask;
+    const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(a.hot_min) ? pol_hot : pol_cold;
+    if (ATT >= 2) prefetch_l2_bulk_hint(a.Q + j * a.ldq + off, R * 128, pol);
+    prefetch_l2_bulk_hint(a.V + j * a.ldv + off, R * 128, pol);
   };
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -124,10 +134,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
-            const int64_t j = __shfl_sync(FULL, myj, t + u);
-            if (ATT >= 2) T::load(q[u], A.Q + j * A.ldq + off, lane, A.D);
+            const int raw = __shfl_sync(FULL, myj, t + u);
+            const int64_t j = raw & kIdMask;
+            const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(A.hot_min) ? pol_hot : pol_cold;
+            if (ATT >= 2) T::load_hint(q[u], A.Q + j * A.ldq + off, lane, A.D, pol);
             if (ATT == 1) qs[u] = __ldg(A.Q + j * A.ldq + myc);
-            if (RX == 0) T::load(h[u], A.V + j * A.ldv + off, lane, A.D);
+            if (RX == 0) T::load_hint(h[u], A.V + j * A.ldv + off, lane, A.D, pol);
             else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
           }
         }
@@ -140,12 +152,25 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
               e = sd + qs[u];
             } else {
               float part[NCH];
+              unsigned mask = 0u;
 #pragma unroll
               for (int k = 0; k < NCH; ++k) part[k] = 0.0f;
 #pragma unroll
               for (int r = 0; r < R; ++r) {
-                if (ATT == 3) part[r / RPC] = fmaf(ar[r], lrelu01(pr[r] + q[u][r]), part[r / RPC]);
-                else part[r / RPC] = fmaf(pr[r], q[u][r], part[r / RPC]);
+                if (ATT == 3) {
+                  const float z = pr[r] + q[u][r];
+                  if (z > 0.0f) mask |= 1u << r;
+                  part[r / RPC] = fmaf(ar[r], lrelu01(z), part[r / RPC]);
+                } else {
+                  part[r / RPC] = fmaf(pr[r], q[u][r], part[r / RPC]);
+                }
+              }
+              if (ATT == 3 && A.esign) {
+                // 1 bit per element of P_i + Q_j, saved for the backward: leaky-relu is piecewise
+                // linear, so neither backward pass needs z itself, only lrelu'(z)
+                const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
+                if (SBPL == 1) A.esign[so] = static_cast<unsigned char>(mask);
+                else *reinterpret_cast<unsigned short*>(A.esign + so) = static_cast<unsigned short>(mask);
               }
               e = T::reduce_own(part, lane);
             }
@@ -273,10 +298,14 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
   constexpr int PF = (T::kVec && RX == 0) ? EDIS_PF : 0;
-  auto prefetch_src = [](const LayerArgs& a, int j, int off) {
+  const uint64_t pol_hot = A.hot_min <= 3 ? l2_policy_evict_last() : l2_policy_evict_normal();
+  const uint64_t pol_cold = A.hot_min <= 3 ? l2_policy_evict_first() : l2_policy_evict_normal();
+  auto prefetch_src = [&](const LayerArgs& a, int raw, int off) {
     // this lane's edge: pull the source row's score part and value part (R*128 bytes each) into L2
-    if (ATT >= 2) prefetch_l2_bulk(a.Q + static_cast<int64_t>(j) * a.ldq + off, R * 128);
-    prefetch_l2_bulk(a.V + static_cast<int64_t>(j) * a.ldv + off, R * 128);
+    const int64_t j = raw & kIdMask;
+    const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(a.hot_min) ? pol_hot : pol_cold;
+    if (ATT == 2) prefetch_l2_bulk_hint(a.Q + j * a.ldq + off, R * 128, pol);
+    prefetch_l2_bulk_hint(a.V + j * a.ldv + off, R * 128, pol);
   };
   constexpr int SBPL = (R + 7) / 8;   // sign bytes per lane per edge
   const int lane = threadIdx.x & 31;
@@ -359,14 +388,23 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
           for (int u = 0; u < U; ++u)
             if (lane == t + u + PF && lane < cnt) prefetch_src(A, myj, off);
         }
-        float q[U][R], h[U][R], ev[U], gx[U], xj[U][RXA];
+        float q[ATT == 2 ? U : 1][R], h[U][R], ev[U], gx[U], xj[U][RXA];
+        unsigned sg[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
-            const int64_t j = __shfl_sync(FULL, myj, t + u);
+            const int raw = __shfl_sync(FULL, myj, t + u);
+            const int64_t j = raw & kIdMask;
+            const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(A.hot_min) ? pol_hot : pol_cold;
             const int64_t edge = eb + t + u;
-            if (ATT >= 2) T::load(q[u], A.Q + j * A.ldq + off, lane, A.D);
-            if (RX == 0) T::load(h[u], A.V + j * A.ldv + off, lane, A.D);
+            if (ATT == 2) T::load_hint(q[u], A.Q + j * A.ldq + off, lane, A.D, pol);
+            if (ATT == 3) {
+              // the forward's sign record of P_i + Q_j replaces the gather of Q_j (2 KB -> 64 B per edge)
+              const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
+              sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
+                                : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
+            }
+            if (RX == 0) T::load_hint(h[u], A.V + j * A.ldv + off, lane, A.D, pol);
             else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
             ev[u] = __ldg(A.edge_e + edge * A.C + myc);
             gx[u] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + myc) : 0.0f;
@@ -405,28 +443,16 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
             }
             if (ATT == 1) dsd += de;
             if (ATT >= 2) {
-              unsigned mask = 0u;
 #pragma unroll
               for (int k = 0; k < NCH; ++k) {
                 const float d = T::from_owner(de, k, lane);
                 const float d001 = 0.01f * d;
 #pragma unroll
                 for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
-                  if (ATT == 3) {
-                    // dP accumulates U = sum_j de_ij lrelu'(z_ijd); scaled by a once per row
-                    const bool pos = pr[r] + q[u][r] > 0.0f;
-                    dP[r] += pos ? d : d001;
-                    if (pos) mask |= 1u << r;
-                  } else {
-                    dP[r] = fmaf(d, q[u][r], dP[r]);
-                  }
+                  // att 3: dP accumulates U = sum_j de_ij lrelu'(z_ijd); scaled by a once per row
+                  if (ATT == 3) dP[r] += ((sg[u] >> r) & 1u) ? d : d001;
+                  else dP[r] = fmaf(d, q[ATT == 2 ? u : 0][r], dP[r]);
                 }
-              }
-              if (ATT == 3) {
-                // 1 bit per element: the source pass needs lrelu'(P_i + Q_j), not P_i itself
-                const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
-                if (SBPL == 1) A.esign[so] = static_cast<unsigned char>(mask);
-                else *reinterpret_cast<unsigned short*>(A.esign + so) = static_cast<unsigned short>(mask);
               }
             }
           }
@@ -463,9 +489,13 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int SBPL = (R + 7) / 8;
   constexpr int PF = T::kVec ? EDIS_PF_SRC : 0;
-  auto prefetch_dst = [](const LayerArgs& a, int i, int off) {
-    if (ATT == 2) prefetch_l2_bulk(a.P + static_cast<int64_t>(i) * a.ldp + off, R * 128);
-    if (HASV) prefetch_l2_bulk(a.gh + static_cast<int64_t>(i) * a.C * a.D + off, R * 128);
+  const uint64_t pol_hot = A.hot_min <= 3 ? l2_policy_evict_last() : l2_policy_evict_normal();
+  const uint64_t pol_cold = A.hot_min <= 3 ? l2_policy_evict_first() : l2_policy_evict_normal();
+  auto prefetch_dst = [&](const LayerArgs& a, int raw, int off) {
+    const int64_t i = raw & kIdMask;
+    const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(a.hot_min) ? pol_hot : pol_cold;
+    if (ATT == 2) prefetch_l2_bulk_hint(a.P + i * a.ldp + off, R * 128, pol);
+    if (HASV) prefetch_l2_bulk_hint(a.gh + i * a.C * a.D + off, R * 128, pol);
   };
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
@@ -509,15 +539,17 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
 #pragma unroll
         for (int u = 0; u < U; ++u) {
           if (t + u < cnt) {
-            const int64_t i = __shfl_sync(FULL, myi, t + u);
+            const int raw = __shfl_sync(FULL, myi, t + u);
+            const int64_t i = raw & kIdMask;
+            const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(A.hot_min) ? pol_hot : pol_cold;
             const int64_t edge = __shfl_sync(FULL, mye, t + u);
-            if (ATT == 2) T::load(pg[u], A.P + i * A.ldp + off, lane, A.D);
+            if (ATT == 2) T::load_hint(pg[u], A.P + i * A.ldp + off, lane, A.D, pol);
             if (ATT == 3) {
               const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
               sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
                                 : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
             }
-            if (HASV) T::load(dh[u], A.gh + i * CD + off, lane, A.D);
+            if (HASV) T::load_hint(dh[u], A.gh + i * CD + off, lane, A.D, pol);
 #pragma unroll
             for (int k = 0; k < NCH; ++k) {
               if (HASV) ad[u][k] = __ldg(A.edge_rec + edge * 2 * A.C + cidx[k]);
@@ -589,7 +621,7 @@ __global__ void __launch_bounds__(256) k_sage_bwd_src_x(const LayerArgs A) {
       const int myi = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
       const int mye = lane < cnt ? __ldg(A.eid + eb + lane) : 0;
       for (int t = 0; t < cnt; ++t) {
-        const int64_t i = __shfl_sync(FULL, myi, t);
+        const int64_t i = __shfl_sync(FULL, myi, t) & kIdMask;
         const int64_t edge = __shfl_sync(FULL, mye, t);
         for (int c = 0; c < A.C; ++c) {
           const float ad = __ldg(A.edge_rec + edge * 2 * A.C + c);
@@ -627,7 +659,10 @@ static int launch_pass(Pass pass, const edis_graph* g, LayerArgs A, cudaStream_t
   A.items = s.items;
   A.n_units = s.n_items * A.G;
   if (pass == Pass::Fwd) return launch_persistent(&k_disga_fwd<T, ATT, RX, U>, g, A, st);
-  if (pass == Pass::BwdDst) return launch_persistent(&k_disga_bwd_dst<T, ATT, RX, U>, g, A, st);
+  if (pass == Pass::BwdDst) {
+    constexpr int UB = (ATT == 3 && RX == 0 && T::kVec && T::KV == 4) ? EDIS_UB_KV4 : U;
+    return launch_persistent(&k_disga_bwd_dst<T, ATT, RX, UB>, g, A, st);
+  }
   if (RX == 0) return launch_persistent(&k_disga_bwd_src<T, ATT, true, U>, g, A, st);
   return launch_persistent(&k_disga_bwd_src<T, ATT, false, 4>, g, A, st);
 }
@@ -712,6 +747,8 @@ static void fill_common(LayerArgs& A, const edis_layer_desc* d, const float* P, 
   A.partial = static_cast<float*>(workspace);
   A.training = d->training && d->p > 0.0f;
   A.plain = (d->flags & EDIS_FLAG_PLAIN_MEAN) ? 1 : 0;
+  static const int hot_env = env_int("EDIS_HOT_MIN", 2);
+  A.hot_min = hot_env;
   A.p = d->p;
   A.inv_keep = 1.0f / (1.0f - d->p);
   A.seed = d->seed;
@@ -729,13 +766,14 @@ static int check_ws(const edis_graph* g, int64_t pw, void* workspace, int64_t by
 
 static unsigned nblk(int64_t total) { return static_cast<unsigned>((total + 255) / 256); }
 
-// Layout of the edge scratch `edge_rec`: E x 2C floats (alpha_drop, d logit), then for att 3 the
-// sign records, (C*D-bit masks stored per (edge, channel group, lane)): at most E*C*32 bytes.
-static int64_t rec_float_bytes(const edis_graph* g, const edis_layer_desc* d) {
-  return g->e * 2 * static_cast<int64_t>(d->C) * static_cast<int64_t>(sizeof(float));
-}
+// Edge scratch `edge_rec` (dst pass -> src pass): E x 2C floats (alpha_drop, d logit).
 static int64_t rec_total_bytes(const edis_graph* g, const edis_layer_desc* d) {
-  return rec_float_bytes(g, d) + (d->att == 3 ? g->e * static_cast<int64_t>(d->C) * 32 : 0) + 64;
+  return g->e * 2 * static_cast<int64_t>(d->C) * static_cast<int64_t>(sizeof(float)) + 64;
+}
+// Sign record `esign` (att 3, forward -> backward): one bit per element of P_i + Q_j, stored per
+// (edge, channel group, lane); at most E*C*32 bytes (the lane-strided layouts pad D to 32*ND).
+static int64_t sign_total_bytes(const edis_graph* g, const edis_layer_desc* d) {
+  return d->att == 3 ? g->e * static_cast<int64_t>(d->C) * 32 + 64 : 0;
 }
 
 // shared tail of the two backward entry points: score-side source pass + combines
@@ -768,11 +806,16 @@ extern "C" int64_t edis_disga_rec_bytes(const edis_graph* g, const edis_layer_de
   return rec_total_bytes(g, d);
 }
 
+extern "C" int64_t edis_disga_sign_bytes(const edis_graph* g, const edis_layer_desc* d) {
+  if (!g || !d || d->C < 1) return EDIS_ERR_ARG;
+  return sign_total_bytes(g, d);
+}
+
 extern "C" int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
                               int64_t ldp, const float* Q, int64_t ldq, const float* a,
                               const float* V, int64_t ldv, const float* bias, float* out,
-                              float* hpre, float* edge_e, float* stats, void* workspace,
-                              int64_t workspace_bytes, void* stream) {
+                              float* hpre, float* edge_e, float* stats, uint8_t* esign,
+                              void* workspace, int64_t workspace_bytes, void* stream) {
   int rc = check_desc(d, "edis_disga_fwd");
   if (rc) return rc;
   EDIS_CHECK_ARG(g && P && Q && V && out && hpre && edge_e && stats, "edis_disga_fwd: null pointer");
@@ -789,6 +832,7 @@ extern "C" int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d, con
   A.nbr = g->col;
   A.bias = bias;
   A.out = out; A.hpre = hpre; A.edge_e = edge_e; A.stats = stats;
+  A.esign = esign;
   A.pwidth = pw;
   rc = launch_layer(Pass::Fwd, g, A, d->att, st);
   if (rc) return rc;
@@ -803,7 +847,8 @@ extern "C" int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d, con
 static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc* d, const float* P,
                               int64_t ldp, const float* Q, int64_t ldq, const float* a,
                               const float* V, int64_t ldv, const float* bias, const float* hpre,
-                              const float* edge_e, const float* stats, const float* g_out,
+                              const float* edge_e, const float* stats, const uint8_t* esign,
+                              const float* g_out,
                               const float* g_edge_e, float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gV, int64_t ldgv,
                               float* edge_rec, float* gh, void* workspace, int64_t workspace_bytes,
                               void* stream) {
@@ -813,6 +858,7 @@ static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc
                  "edis_disga_bwd: null pointer");
   EDIS_CHECK_ARG(d->Dv == d->D, "edis_disga_bwd: Dv must equal D");
   EDIS_CHECK_ARG(d->att != 3 || (a && ga), "edis_disga_bwd: att=3 needs a and ga");
+  EDIS_CHECK_ARG(d->att != 3 || esign, "edis_disga_bwd: att=3 needs the forward's sign record (esign)");
   EDIS_CHECK_ARG(d->D % 4 != 0 || (vec_ok(V, ldv) && (d->att == 1 || (vec_ok(P, ldp) && vec_ok(Q, ldq))) &&
                                    vec_ok(g_out, 4) && vec_ok(gV, ldgv) && vec_ok(gh, 4) &&
                                    (d->att == 1 || (vec_ok(gP, ldgp) && vec_ok(gQ, ldgq)))),
@@ -827,7 +873,7 @@ static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc
   A.hpre = const_cast<float*>(hpre); A.edge_e = const_cast<float*>(edge_e); A.stats = const_cast<float*>(stats);
   A.g_out = g_out; A.g_edge_e = g_edge_e;
   A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gV; A.edge_rec = edge_rec; A.gh = gh;
-  A.esign = reinterpret_cast<unsigned char*>(edge_rec) + rec_float_bytes(g, d);
+  A.esign = const_cast<uint8_t*>(esign);
   A.ldgp = ldgp; A.ldgq = ldgq; A.ldgv = ldgv;
   A.pwidth = pw;
   if (phases & 1) {
@@ -848,12 +894,13 @@ static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc
 #define EDIS_BWD_ARGS                                                                               \
   const edis_graph *g, const edis_layer_desc *d, const float *P, int64_t ldp, const float *Q,       \
       int64_t ldq, const float *a, const float *V, int64_t ldv, const float *bias,                  \
-      const float *hpre, const float *edge_e, const float *stats, const float *g_out,               \
+      const float *hpre, const float *edge_e, const float *stats, const uint8_t *esign,             \
+      const float *g_out,                                                                           \
       const float *g_edge_e, float *gP, int64_t ldgp, float *gQ, int64_t ldgq, float *ga,         \
       float *gV, int64_t ldgv, float *edge_rec,                                                     \
       float *gh, void *workspace, int64_t workspace_bytes, void *stream
 #define EDIS_BWD_PASS                                                                               \
-  g, d, P, ldp, Q, ldq, a, V, ldv, bias, hpre, edge_e, stats, g_out, g_edge_e, gP, ldgp, gQ, ldgq, ga, gV, ldgv, \
+  g, d, P, ldp, Q, ldq, a, V, ldv, bias, hpre, edge_e, stats, esign, g_out, g_edge_e, gP, ldgp, gQ, ldgq, ga, gV, ldgv, \
       edge_rec, gh, workspace, workspace_bytes, stream
 
 extern "C" int edis_disga_bwd(EDIS_BWD_ARGS) { return disga_bwd_impl(3, EDIS_BWD_PASS); }
@@ -865,8 +912,8 @@ extern "C" int edis_disga_bwd_src(EDIS_BWD_ARGS) { return disga_bwd_impl(2, EDIS
 extern "C" int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
                                    int64_t ldp, const float* Q, int64_t ldq, const float* a,
                                    const float* X, int64_t ldx, float* neigh, float* edge_e,
-                                   float* stats, void* workspace, int64_t workspace_bytes,
-                                   void* stream) {
+                                   float* stats, uint8_t* esign, void* workspace,
+                                   int64_t workspace_bytes, void* stream) {
   int rc = check_desc(d, "edis_disga_sage_fwd");
   if (rc) return rc;
   EDIS_CHECK_ARG(g && P && Q && X && neigh && edge_e && stats, "edis_disga_sage_fwd: null pointer");
@@ -881,6 +928,7 @@ extern "C" int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d
   fill_common(A, d, P, ldp, Q, ldq, a, X, ldx, workspace);
   A.nbr = g->col;
   A.hpre = neigh; A.edge_e = edge_e; A.stats = stats;
+  A.esign = esign;
   A.pwidth = pw;
   rc = launch_sage(Pass::Fwd, g, A, d->att, st);
   if (rc) return rc;
@@ -895,7 +943,8 @@ extern "C" int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d
 extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d, const float* P,
                                    int64_t ldp, const float* Q, int64_t ldq, const float* a,
                                    const float* X, int64_t ldx, const float* neigh,
-                                   const float* edge_e, const float* stats, const float* g_neigh,
+                                   const float* edge_e, const float* stats, const uint8_t* esign,
+                                   const float* g_neigh,
                                    const float* g_edge_e, float* gP, int64_t ldgp, float* gQ,
                                    int64_t ldgq, float* ga, float* gX, float* edge_rec, float* gh,
                                    void* workspace, int64_t workspace_bytes, void* stream) {
@@ -906,6 +955,7 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
                      edge_rec && gh, "edis_disga_sage_bwd: null pointer");
   EDIS_CHECK_ARG(d->Dv >= 1 && d->Dv <= 256, "edis_disga_sage_bwd: F=%d (Dv) must be in [1, 256]", d->Dv);
   EDIS_CHECK_ARG(d->att != 3 || (a && ga), "edis_disga_sage_bwd: att=3 needs a and ga");
+  EDIS_CHECK_ARG(d->att != 3 || esign, "edis_disga_sage_bwd: att=3 needs the forward's sign record (esign)");
   const int CD = d->C * d->D;
   const int64_t pw = 2 * static_cast<int64_t>(CD) + 2 * d->C + d->Dv;
   if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_sage_bwd"))) return rc;
@@ -915,7 +965,7 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
   A.hpre = const_cast<float*>(neigh); A.edge_e = const_cast<float*>(edge_e); A.stats = const_cast<float*>(stats);
   A.g_out = g_neigh; A.g_edge_e = g_edge_e;
   A.gP = gP; A.gQ = gQ; A.ga = ga; A.gV = gX; A.edge_rec = edge_rec; A.gh = gh;
-  A.esign = reinterpret_cast<unsigned char*>(edge_rec) + rec_float_bytes(g, d);
+  A.esign = const_cast<uint8_t*>(esign);
   A.ldgp = ldgp; A.ldgq = ldgq; A.ldgv = d->Dv;
   A.pwidth = pw;
   const int ph = d->flags & EDIS_FLAG_PHASE_MASK;   // 0 = all passes

@@ -107,6 +107,41 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
   asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
 }
 
+// ---- L2 residency control for the gathers -------------------------------------------------
+// The device copies of `col` / `cscrow` carry a 2-bit "heat" level of the neighbour in bits 30-31
+// (3: among the 4K most-gathered nodes, 2: top 16K, 1: top 64K, 0: the rest).  Rows of hot
+// neighbours are loaded with an evict_last L2 policy, all other gathered rows with evict_first,
+// so the hub rows of a power-law graph stay resident in the 126 MB L2 instead of competing
+// with the streaming rows under plain LRU.
+constexpr int kHeatShift = 30;
+constexpr int kIdMask = (1 << kHeatShift) - 1;
+__device__ __forceinline__ uint64_t l2_policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ float4 ldg4_hint(const float* ptr, uint64_t pol) {
+  float4 v;
+  asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(ptr), "l"(pol));
+  return v;
+}
+__device__ __forceinline__ void prefetch_l2_bulk_hint(const void* p, unsigned bytes, uint64_t pol) {
+  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol)
+               : "memory");
+}
+
 int launch_grid(const void* kernel, int block, size_t smem, int sm_count);
 
 }  // namespace edis

@@ -2,6 +2,7 @@
 // Integer work: must be bit-exact against the reference's `load_data` pipeline
 // (/root/reference/data_load.py:39-77, utils.py:163-170) -- see include/edis.h.
 #include <algorithm>
+#include <functional>
 #include <cmath>
 #include <cstdarg>
 #include <cstring>
@@ -267,9 +268,31 @@ extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, c
   if ((rc = upload(&g->src.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->src.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->rowptr, g->h_rowptr, n + 1)) != EDIS_OK) return fail(rc);
-  if ((rc = upload(&g->col, g->h_col, e)) != EDIS_OK) return fail(rc);
+  // device copies of the neighbour arrays carry the neighbour's heat level in bits 30-31
+  // (see edis_common.cuh); the host mirrors stay plain
+  std::vector<int32_t> dcol(g->h_col, g->h_col + e), dcscrow(g->h_cscrow, g->h_cscrow + e);
+  if (n_cols < (int64_t(1) << kHeatShift) && e > 0) {
+    auto heat_of = [](const int64_t* ptr, int64_t count) {
+      std::vector<int64_t> deg(count);
+      for (int64_t i = 0; i < count; ++i) deg[i] = ptr[i + 1] - ptr[i];
+      std::vector<int64_t> srt(deg);
+      std::sort(srt.begin(), srt.end(), std::greater<int64_t>());
+      auto thr = [&](int64_t k) { return k < count ? std::max<int64_t>(srt[k], 2) : int64_t(2); };
+      const int64_t t3 = thr(4096), t2 = thr(16384), t1 = thr(65536);
+      std::vector<uint8_t> h(count);
+      for (int64_t i = 0; i < count; ++i) h[i] = deg[i] > t3 ? 3 : deg[i] > t2 ? 2 : deg[i] > t1 ? 1 : 0;
+      return h;
+    };
+    const std::vector<uint8_t> hsrc = heat_of(g->h_cscptr, n_cols);   // how often a source row is gathered
+    const std::vector<uint8_t> hdst = heat_of(g->h_rowptr, n);        // ... a destination row (src pass)
+    for (int64_t k = 0; k < e; ++k) {
+      dcol[k] |= static_cast<int32_t>(static_cast<uint32_t>(hsrc[g->h_col[k]]) << kHeatShift);
+      dcscrow[k] |= static_cast<int32_t>(static_cast<uint32_t>(hdst[g->h_cscrow[k]]) << kHeatShift);
+    }
+  }
+  if ((rc = upload(&g->col, dcol.data(), e)) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->cscptr, g->h_cscptr, n_cols + 1)) != EDIS_OK) return fail(rc);
-  if ((rc = upload(&g->cscrow, g->h_cscrow, e)) != EDIS_OK) return fail(rc);
+  if ((rc = upload(&g->cscrow, dcscrow.data(), e)) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->csceid, g->h_csceid, e)) != EDIS_OK) return fail(rc);
   cudaSetDevice(prev_dev);
   *out = g;

@@ -74,6 +74,14 @@ struct VecT {
       r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
     }
   }
+  __device__ static __forceinline__ void load_hint(float (&r)[R], const float* base, int lane, int,
+                                                   uint64_t pol) {
+#pragma unroll
+    for (int k = 0; k < KV; ++k) {
+      const float4 v = ldg4_hint(base + (k * 32 + lane) * 4, pol);
+      r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
+    }
+  }
   __device__ static __forceinline__ void store(float* base, const float (&r)[R], int lane, int) {
 #pragma unroll
     for (int k = 0; k < KV; ++k)
@@ -90,7 +98,7 @@ struct VecT {
 // ScaT: any D <= 32*ND, one channel per warp, lane-strided scalar accesses.
 template <int ND_>
 struct ScaT {
-  static constexpr int NCH = 1, RPC = ND_, R = ND_, CPW = 1;
+  static constexpr int NCH = 1, RPC = ND_, R = ND_, CPW = 1, KV = 0;
   static constexpr bool kVec = false;
   __device__ static __forceinline__ int ch(int, int) { return 0; }
   __device__ static __forceinline__ bool writer(int lane) { return lane == 0; }
@@ -109,6 +117,9 @@ struct ScaT {
   __device__ static __forceinline__ void load(float (&r)[R], const float* base, int lane, int D) {
 #pragma unroll
     for (int k = 0; k < ND_; ++k) r[k] = (k * 32 + lane < D) ? __ldg(base + k * 32 + lane) : 0.0f;
+  }
+  __device__ static __forceinline__ void load_hint(float (&r)[R], const float* base, int lane, int D, uint64_t) {
+    load(r, base, lane, D);
   }
   __device__ static __forceinline__ void store(float* base, const float (&r)[R], int lane, int D) {
 #pragma unroll

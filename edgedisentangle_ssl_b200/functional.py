@@ -84,6 +84,14 @@ def _edge_rec(graph, d, device):
     return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
 
 
+def _sign_rec(graph, d, device, wanted):
+    """att 3: the forward's 1-bit-per-element record of sign(P_i + Q_j), kept for the backward."""
+    if d.att != 3 or not wanted:
+        return None
+    nbytes = check(lib.edis_disga_sign_bytes(graph.handle, ctypes.byref(d)), "edis_disga_sign_bytes")
+    return torch.empty(int(nbytes), dtype=torch.uint8, device=device)
+
+
 def _workspace(graph, width, like):
     nbytes = graph.workspace_bytes(width)
     return torch.empty(nbytes, dtype=torch.uint8, device=like.device), nbytes
@@ -122,19 +130,20 @@ class DisGAFused(torch.autograd.Function):
         stats = torch.empty(n, 2 * C, dtype=torch.float32, device=proj.device)
         ws, nbytes = _workspace(graph, CD + 2 * C, proj)
         d = _desc(att, C, D, training, p, seed)
+        esign = _sign_rec(graph, d, proj.device, any(ctx.needs_input_grad))
         with _timed("disga_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
             check(lib.edis_disga_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a),
                                      _off(proj, off_v), ld, _ptr(bias), _ptr(out), _ptr(hpre), _ptr(edge_e),
-                                     _ptr(stats), _ptr(ws), nbytes, _stream()), "edis_disga_fwd")
+                                     _ptr(stats), _ptr(esign), _ptr(ws), nbytes, _stream()), "edis_disga_fwd")
         ctx.graph, ctx.d, ctx.offs = graph, d, (off_p, off_q, off_v)
         ctx.has_a, ctx.has_bias = a is not None, bias is not None
-        ctx.save_for_backward(proj, sdst, ssrc, a, bias, hpre, edge_e, stats)
+        ctx.save_for_backward(proj, sdst, ssrc, a, bias, hpre, edge_e, stats, esign)
         ctx.set_materialize_grads(False)
         return out, edge_e
 
     @staticmethod
     def backward(ctx, g_out, g_edge_e):
-        proj, sdst, ssrc, a, bias, hpre, edge_e, stats = ctx.saved_tensors
+        proj, sdst, ssrc, a, bias, hpre, edge_e, stats, esign = ctx.saved_tensors
         graph, d = ctx.graph, ctx.d
         C, D, att = d.C, d.D, d.att
         CD = C * D
@@ -171,7 +180,7 @@ class DisGAFused(torch.autograd.Function):
         gh = torch.empty(n, CD, dtype=torch.float32, device=dev)
         ws, nbytes = _workspace(graph, 2 * CD + 2 * C, proj)
         args = (graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _off(proj, off_v), ld, _ptr(bias),
-                _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(g_out), _ptr(g_edge_e), gP, ldgp, gQ, ldgq,
+                _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_out), _ptr(g_edge_e), gP, ldgp, gQ, ldgq,
                 _ptr(ga), _off(g_proj, off_v), W, _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream())
         with _timed("disga_bwd_dst", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
             check(lib.edis_disga_bwd_dst(*args), "edis_disga_bwd_dst")
@@ -217,19 +226,21 @@ class SageFused(torch.autograd.Function):
         d = _desc(att, C, D, training, p, seed)
         d.Dv = Fin
         d.flags = (_lib.FLAG_PLAIN_MEAN if plain else 0) | (0 if ctx.needs_input_grad[10] else _lib.FLAG_NO_GX)
+        esign = _sign_rec(graph, d, X.device, any(ctx.needs_input_grad))
         with _timed("disga_sage_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
             check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X), ldx,
-                                          _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(ws), nbytes, _stream()),
+                                          _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(ws), nbytes,
+                                          _stream()),
                   "edis_disga_sage_fwd")
         ctx.graph, ctx.d, ctx.offs, ctx.ldx = graph, d, (off_p, off_q), ldx
         ctx.has_a = a is not None
-        ctx.save_for_backward(proj, sdst, ssrc, a, X, agg, edge_e, stats)
+        ctx.save_for_backward(proj, sdst, ssrc, a, X, agg, edge_e, stats, esign)
         ctx.set_materialize_grads(False)
         return agg, edge_e
 
     @staticmethod
     def backward(ctx, g_agg, g_edge_e):
-        proj, sdst, ssrc, a, X, agg, edge_e, stats = ctx.saved_tensors
+        proj, sdst, ssrc, a, X, agg, edge_e, stats, esign = ctx.saved_tensors
         graph, d = ctx.graph, ctx.d
         C, D, att, Fin = d.C, d.D, d.att, d.Dv
         CD = C * D
@@ -275,7 +286,7 @@ class SageFused(torch.autograd.Function):
             d.flags = base | bit
             with _timed(name, graph, nl):
                 check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X),
-                                              ctx.ldx, _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(g_agg),
+                                              ctx.ldx, _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_agg),
                                               _ptr(g_edge_e), gP, ldgp, gQ, ldgq, _ptr(ga), _ptr(gX),
                                               _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream()),
                       "edis_disga_sage_bwd")

@@ -118,13 +118,21 @@ typedef struct {
 #define EDIS_FLAG_PHASE_GX 16
 #define EDIS_FLAG_PHASE_MASK 28
 
-/* Forward.  Saved for backward: edge_e[E,C], stats[N,2C] (row sums: sum w, sum w*mask), hpre.
- * out / hpre: [N, C*Dv] contiguous.  workspace >= edis_graph_workspace_bytes(g, C*Dv + 2*C). */
+/* Forward.  Saved for backward: edge_e[E,C], stats[N,2C] (row sums: sum w, sum w*mask), hpre and,
+ * for att 3, esign.
+ * out / hpre: [N, C*Dv] contiguous.  workspace >= edis_graph_workspace_bytes(g, C*Dv + 2*C).
+ *   esign  att 3 only, edis_disga_sign_bytes(g, d) bytes or NULL (inference: nothing is saved):
+ *          one SIGN BIT per element of P_i + Q_j for every edge.  Leaky-relu is piecewise linear,
+ *          so both backward passes need only lrelu'(z), never z: the destination pass reads 64 B
+ *          per edge instead of re-gathering Q_j (2 KB per edge at C*D = 512), the source pass
+ *          64 B instead of gathering P_i. */
 int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d,
                    const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
                    const float* V, int64_t ldv, const float* bias,
-                   float* out, float* hpre, float* edge_e, float* stats,
+                   float* out, float* hpre, float* edge_e, float* stats, uint8_t* esign,
                    void* workspace, int64_t workspace_bytes, void* stream);
+/* bytes of the att-3 sign record for this graph / layer (0 for att 1 / 2; same for the SAGE entry) */
+int64_t edis_disga_sign_bytes(const edis_graph* g, const edis_layer_desc* d);
 
 /* Backward of edis_disga_fwd (replaces autograd through layers.py:349-416: the
  * `index_put_(accumulate)` gathers' backward and scatter_add backward).
@@ -133,16 +141,15 @@ int edis_disga_fwd(const edis_graph* g, const edis_layer_desc* d,
  *                  (so they can be column blocks of one gradient buffer of the projection GEMM)
  *   ga[C,D]        grad wrt a (att 3), accumulated with atomics: caller zero-fills
  *   gV[N,C*Dv]     grad wrt V, row stride ldgv (grad wrt bias = column sum of gh; caller reduces)
+ *   esign          the sign record the forward wrote (att 3: required; else NULL)
  *   edge_rec       scratch of edis_disga_rec_bytes(g, d) bytes handed from the dst pass to the
- *                  src pass: per edge (alpha_drop, d logit)[2C] and, for att 3, one SIGN BIT per
- *                  element of P_i + Q_j (leaky-relu is piecewise linear, so the src pass needs
- *                  only lrelu'(z): 64 B/edge instead of gathering P_i, 2 KB/edge at C*D=512);
+ *                  src pass: per edge (alpha_drop, d logit)[2C];
  *                  gh[N,C*Dv] scratch node tensor (grad wrt pre-activation)
  * workspace >= edis_graph_workspace_bytes(g, 2*C*max(D,Dv) + 2*C). */
 int edis_disga_bwd(const edis_graph* g, const edis_layer_desc* d,
                    const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
                    const float* V, int64_t ldv, const float* bias,
-                   const float* hpre, const float* edge_e, const float* stats,
+                   const float* hpre, const float* edge_e, const float* stats, const uint8_t* esign,
                    const float* g_out, const float* g_edge_e,
                    float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gV, int64_t ldgv,
                    float* edge_rec, float* gh,
@@ -155,7 +162,7 @@ int64_t edis_disga_rec_bytes(const edis_graph* g, const edis_layer_desc* d);
 int edis_disga_bwd_dst(const edis_graph* g, const edis_layer_desc* d,
                        const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
                        const float* V, int64_t ldv, const float* bias,
-                       const float* hpre, const float* edge_e, const float* stats,
+                       const float* hpre, const float* edge_e, const float* stats, const uint8_t* esign,
                        const float* g_out, const float* g_edge_e,
                        float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gV, int64_t ldgv,
                        float* edge_rec, float* gh,
@@ -163,7 +170,7 @@ int edis_disga_bwd_dst(const edis_graph* g, const edis_layer_desc* d,
 int edis_disga_bwd_src(const edis_graph* g, const edis_layer_desc* d,
                        const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
                        const float* V, int64_t ldv, const float* bias,
-                       const float* hpre, const float* edge_e, const float* stats,
+                       const float* hpre, const float* edge_e, const float* stats, const uint8_t* esign,
                        const float* g_out, const float* g_edge_e,
                        float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gV, int64_t ldgv,
                        float* edge_rec, float* gh,
@@ -179,12 +186,12 @@ int edis_disga_bwd_src(const edis_graph* g, const edis_layer_desc* d,
 int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d,
                         const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
                         const float* X, int64_t ldx,
-                        float* neigh, float* edge_e, float* stats,
+                        float* neigh, float* edge_e, float* stats, uint8_t* esign,
                         void* workspace, int64_t workspace_bytes, void* stream);
 int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d,
                         const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
                         const float* X, int64_t ldx,
-                        const float* neigh, const float* edge_e, const float* stats,
+                        const float* neigh, const float* edge_e, const float* stats, const uint8_t* esign,
                         const float* g_neigh, const float* g_edge_e,
                         float* gP, int64_t ldgp, float* gQ, int64_t ldgq, float* ga, float* gX,
                         float* edge_rec, float* gh,
