@@ -210,28 +210,6 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------- GPU arm
-def algorithmic_bytes(n, e, C, D, att, feats):
-    """Gather-model bytes per launch, fp32.  Plan "proj" (project, then gather V_j): SURVEY 8(d).
-    Plan "agg" (aggregate the raw input, project afterwards; DESIGN.md e): the aggregated operand
-    gathered per edge is F floats instead of C*D, the source pass reads sign bits instead of P_i.
-    Returns {kernel name: [bytes for layer 1, layer 2]}."""
-    cd = C * D
-    score = 4 * C if att == 1 else 4 * cd
-    out = {"disga_fwd": [e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n] * 2,
-           "disga_bwd_dst": [e * (score + 4 * cd + 4 * C + 4) + 8 * cd * n] * 2,
-           "disga_bwd_src": [e * (score + 4 * cd) + 4 * cd * n] * 2}
-    sign = cd // 8 if att == 3 else 0
-    for name in ("disga_sage_fwd", "disga_sage_bwd_dst", "disga_sage_bwd_src", "disga_sage_bwd_gx"):
-        out[name] = []
-    for f in feats:
-        out["disga_sage_fwd"].append(e * (score + 4 * f + 4 * C + 4) + n * (score + 4 * C * f + 8 * C))
-        out["disga_sage_bwd_dst"].append(e * (score + 4 * f + 4 * C + 8 * C + sign + 4)
-                                         + n * (score + 12 * C * f + score))
-        out["disga_sage_bwd_src"].append(e * (8 * C + sign + 8 + (score if att == 2 else 0)) + n * score)
-        out["disga_sage_bwd_gx"].append(e * (4 * C * f + 4 * C + 8) + n * 4 * f)
-    return out
-
-
 def main():
     a = parse()
     if a.impl == "reference":
@@ -330,6 +308,7 @@ def main():
     ms_res = timed(False, a.steps)
     Fn.TIMER.enabled = False
     kernel_list = Fn.TIMER.durations_ms()
+    kernel_bytes = Fn.TIMER.bytes()
     plan = os.environ.get("EDIS_AT_PLAN") or "proj"
     launches = Fn.TIMER.launches
     step(True)
@@ -350,25 +329,34 @@ def main():
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    alg = algorithmic_bytes(graph.n, graph.e, a.nhead, a.nhid, a.att, [a.feat, a.nhid])
-    # per kernel: launches alternate layer 1 / layer 2 in forward order (backward: layer 2 first)
+    # per kernel: SURVEY 8(d) algorithmic bytes and this implementation's own byte model, both
+    # recorded per call by functional.kernel_bytes (layer 1 and layer 2 may run different plans)
     per = {}
     for k, v in kernel_list.items():
-        if k not in alg or not v:
+        if not v:
             continue
-        order = [0, 1] if "fwd" in k else [1, 0]
-        if k == "disga_sage_bwd_gx":
-            order = [1]                      # only the layer whose input needs a gradient launches it
         ms = np.array(v)
-        tot_b = sum(alg[k][order[i % len(order)]] for i in range(len(ms)))
-        per[k] = {"ms_per_launch": float(ms.mean()), "gbs": tot_b / (ms.sum() * 1e-3) / 1e9,
-                  "bytes_per_launch": tot_b / len(ms), "ms_per_step": float(ms.sum() / a.steps)}
+        alg_b = sum(m["alg"] for m in kernel_bytes[k])
+        mov_b = sum(m["moved"] for m in kernel_bytes[k])
+        per[k] = {"ms_per_launch": float(ms.mean()), "launches_per_step": len(ms) / a.steps,
+                  "gbs": alg_b / (ms.sum() * 1e-3) / 1e9, "moved_gbs": mov_b / (ms.sum() * 1e-3) / 1e9,
+                  "bytes_per_launch": alg_b / len(ms), "moved_bytes_per_launch": mov_b / len(ms),
+                  "ms_per_step": float(ms.sum() / a.steps)}
     dom = max(per, key=lambda k: per[k]["ms_per_step"]) if per else None
     roof = None
     if dom:
+        tot_ms = sum(v["ms_per_step"] for v in per.values())
+        tot_alg = sum(v["bytes_per_launch"] * v["launches_per_step"] for v in per.values())
         roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": per[dom]["bytes_per_launch"], "plan": plan, "kernels": per}
+                "algorithmic_bytes_per_launch": per[dom]["bytes_per_launch"],
+                "moved_frac": per[dom]["moved_gbs"] / peak,
+                "note": "achieved = SURVEY 8(d) gather-model bytes of the reference layer / CUDA-event time; "
+                        "moved_* = bytes this implementation must move with no L2 reuse (sign record instead "
+                        "of re-gathered rows, F floats for a shared operand); traffic = ncu DRAM bytes",
+                "all_sparse_kernels": {"ms_per_step": tot_ms, "gbs": tot_alg / (tot_ms * 1e-3) / 1e9,
+                                       "frac": tot_alg / (tot_ms * 1e-3) / 1e9 / peak},
+                "plan": plan, "kernels": per}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath):
             roof["traffic"] = json.load(open(tpath)).get(dom)

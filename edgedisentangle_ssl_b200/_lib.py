@@ -72,6 +72,7 @@ SIGNATURES = {
     "edis_disga_sage_bwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64,
                                     _P, _P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, _P, _P,
                                     c_int64, _P]),
+    "edis_disga_sage_fused_gx": (c_int, [_descp]),
     "edis_pair_score_fwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,
                                     _P, c_int64, _P, _P, _P]),
     "edis_pair_score_bwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,

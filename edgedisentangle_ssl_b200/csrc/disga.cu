@@ -14,7 +14,11 @@
 //     pull on both sides, no float atomics on node tensors, deterministic.
 // Template parameter RX selects the aggregated operand: RX == 0 -> per-channel V[N, C*D]
 // (gnn_type AT / GCN); RX > 0 -> the raw input X[N, F <= 32*RX] shared by all channels
-// (gnn_type SAGE), accumulated lane-strided.
+// (gnn_type SAGE, or AT / GCN run as aggregate-then-project), accumulated lane-strided;
+// RX == -1 -> the same shared operand when F == D on the 128-bit layouts: one float4 of X_j per
+// lane feeds all of the lane's channel slots (256 B gathered per edge instead of C*D*4).
+#include <type_traits>
+
 #include "edis_common.cuh"
 #include "traits.cuh"
 
@@ -33,8 +37,19 @@
 #ifndef EDIS_UB_KV4
 #define EDIS_UB_KV4 2
 #endif
+// source pass on the whole-row path: edges in flight
+#ifndef EDIS_USRC_KV4
+#define EDIS_USRC_KV4 2
+#endif
+// shared-operand 128-bit path (RX == -1), whole-row warps: edges in flight
+#ifndef EDIS_US_KV4
+#define EDIS_US_KV4 2
+#endif
 #ifndef EDIS_MINB
 #define EDIS_MINB 2
+#endif
+#ifndef EDIS_MINB_DST
+#define EDIS_MINB_DST EDIS_MINB
 #endif
 // L2 prefetch distance (edges ahead of the consuming loads) for the 128-bit paths; 0 = off
 #ifndef EDIS_PF
@@ -89,18 +104,25 @@ template <class T, int ATT, int RX, int U>
 __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
-  constexpr int PF = (T::kVec && RX == 0) ? EDIS_PF : 0;
+  constexpr bool SHV = RX < 0;          // shared operand in the 128-bit layout (F == D)
+  constexpr int PF = (T::kVec && RX <= 0) ? EDIS_PF : 0;
   constexpr int SBPL = (R + 7) / 8;   // sign bytes per lane per edge
-  const uint64_t pol_hot = A.hot_min <= 3 ? l2_policy_evict_last() : l2_policy_evict_normal();
-  const uint64_t pol_cold = A.hot_min <= 3 ? l2_policy_evict_first() : l2_policy_evict_normal();
-  auto prefetch_src = [&](const LayerArgs& a, int raw, int off) {
-    // this lane's edge: pull the source row's score part and value part (R*128 bytes each) into L2
+  // The whole warp pulls the row parts of the edge PF steps ahead into L2, one 128-byte line per
+  // lane: lanes [0, R) the score part Q_j, lanes [R, 2R) the value part V_j (R*128 bytes each);
+  // shared operand: F*4 bytes of X_j.
+  constexpr int QL = ATT >= 2 ? R : 0;                 // lines of the score part
+  auto prefetch_src = [&](int raw, int off, int lane) {
     const int64_t j = raw & kIdMask;
-    const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(a.hot_min) ? pol_hot : pol_cold;
-    if (ATT >= 2) prefetch_l2_bulk_hint(a.Q + j * a.ldq + off, R * 128, pol);
-    prefetch_l2_bulk_hint(a.V + j * a.ldv + off, R * 128, pol);
+    const int vl = lane - QL;                          // line of the value part
+    const float* pp = nullptr;
+    if (lane < QL) pp = A.Q + j * A.ldq + off + lane * 32;
+    else if (SHV ? vl * 32 < A.D : vl < R) pp = A.V + j * A.ldv + (SHV ? 0 : off) + vl * 32;
+    if (pp) {
+      if (is_hot(raw, A.hot_min)) prefetch_l2_line<true>(pp); else prefetch_l2_line<false>(pp);
+    }
   };
   const int lane = threadIdx.x & 31;
+  const int xoff = (lane % T::LPCV) * 4;   // SHV: this lane's float4 of the shared operand
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   for (; unit < A.n_units; unit += nwarps) {
@@ -113,7 +135,11 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
     const int64_t srow = static_cast<int64_t>(it.row);
     float pr[R], ar[R], sd = 0.0f;
     if (ATT >= 2) T::load(pr, A.P + srow * A.ldp + off, lane, A.D);
-    if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
+    if (ATT == 3) {
+      T::load(ar, A.a + off, lane, A.D);
+#pragma unroll
+      for (int r = 0; r < R; ++r) ar[r] = -ar[r];
+    }
     if (ATT == 1) sd = __ldg(A.P + srow * A.ldp + myc);
     float acc[R], accx[NACC], ws = 0.0f, wms = 0.0f;
     zero<T>(acc);
@@ -123,30 +149,42 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
     for (int eb = it.beg; eb < it.end; eb += 32) {
       const int cnt = min(32, it.end - eb);
       const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
-      if (PF > 0 && lane < cnt && lane < PF) prefetch_src(A, myj, off);
+      if (PF > 0) {
+#pragma unroll
+        for (int pq = 0; pq < PF; ++pq)
+          if (pq < cnt) prefetch_src(__shfl_sync(FULL, myj, pq), off, lane);
+      }
       for (int t = 0; t < cnt; t += U) {
         if (PF > 0) {
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            if (lane == t + u + PF && lane < cnt) prefetch_src(A, myj, off);
+            if (t + u + PF < cnt) prefetch_src(__shfl_sync(FULL, myj, t + u + PF), off, lane);
         }
-        float q[U][R], h[U][R], qs[U], xj[U][RXA];
+        float q[U][R], h[RX == 0 ? U : 1][R], qs[U], xj[U][RXA];
+        float4 hx[SHV ? U : 1];
+        // a short tail re-reads the last edge of the block (same cache lines) with weight 0
+        // instead of guarding every load / FMA with a branch
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t + u < cnt) {
-            const int raw = __shfl_sync(FULL, myj, t + u);
-            const int64_t j = raw & kIdMask;
-            const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(A.hot_min) ? pol_hot : pol_cold;
-            if (ATT >= 2) T::load_hint(q[u], A.Q + j * A.ldq + off, lane, A.D, pol);
-            if (ATT == 1) qs[u] = __ldg(A.Q + j * A.ldq + myc);
-            if (RX == 0) T::load_hint(h[u], A.V + j * A.ldv + off, lane, A.D, pol);
-            else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
-          }
+          const int raw = __shfl_sync(FULL, myj, min(t + u, cnt - 1));
+          const int64_t j = raw & kIdMask;
+          const float* qp = A.Q + j * A.ldq + off;
+          const float* vp = A.V + j * A.ldv + (SHV ? xoff : off);
+          auto go = [&](auto hot) {
+            constexpr bool H = decltype(hot)::value;
+            if (ATT >= 2) T::template load_pol<H>(q[u], qp, lane, A.D);
+            if (RX == 0) T::template load_pol<H>(h[RX == 0 ? u : 0], vp, lane, A.D);
+            else if (SHV) hx[SHV ? u : 0] = ldg4_pol<H>(vp);
+          };
+          if (is_hot(raw, A.hot_min)) go(std::true_type{}); else go(std::false_type{});
+          if (ATT == 1) qs[u] = __ldg(A.Q + j * A.ldq + myc);
+          if (RX > 0) load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t + u < cnt) {
-            const int64_t edge = eb + t + u;
+          const bool valid = U == 1 || t + u < cnt;
+          {
+            const int64_t edge = eb + min(t + u, cnt - 1);
             float e;
             if (ATT == 1) {
               e = sd + qs[u];
@@ -158,14 +196,15 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
 #pragma unroll
               for (int r = 0; r < R; ++r) {
                 if (ATT == 3) {
-                  const float z = pr[r] + q[u][r];
-                  if (z > 0.0f) mask |= 1u << r;
-                  part[r / RPC] = fmaf(ar[r], lrelu01(z), part[r / RPC]);
+                  // w = -(P_i + Q_j); ar holds -a: a * lrelu(z) = (-a) * min(w, 0.01 w)
+                  const float w = -pr[r] - q[u][r];
+                  mask = sign_push(mask, w);
+                  part[r / RPC] = fmaf(ar[r], fminf(w, 0.01f * w), part[r / RPC]);
                 } else {
                   part[r / RPC] = fmaf(pr[r], q[u][r], part[r / RPC]);
                 }
               }
-              if (ATT == 3 && A.esign) {
+              if (ATT == 3 && A.esign && valid) {
                 // 1 bit per element of P_i + Q_j, saved for the backward: leaky-relu is piecewise
                 // linear, so neither backward pass needs z itself, only lrelu'(z)
                 const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
@@ -174,7 +213,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
               }
               e = T::reduce_own(part, lane);
             }
-            const float w = __expf(sigmoidf_fast(e));
+            const float w = valid ? exp_mufu(sigmoid_mufu(e)) : 0.0f;
             const float ms = A.training ? keep_scale(A.seed, edge * A.C + myc, A.p, A.inv_keep) : 1.0f;
             const float wm = w * ms;
             ws += w;
@@ -184,7 +223,16 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
               for (int k = 0; k < NCH; ++k) {
                 const float wk = T::from_owner(wm, k, lane);
 #pragma unroll
-                for (int r = k * RPC; r < (k + 1) * RPC; ++r) acc[r] = fmaf(wk, h[u][r], acc[r]);
+                for (int r = k * RPC; r < (k + 1) * RPC; ++r) acc[r] = fmaf(wk, h[RX == 0 ? u : 0][r], acc[r]);
+              }
+            } else if (SHV) {
+              const float4 hv = hx[SHV ? u : 0];
+              const float x4[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                const float wk = T::from_owner(wm, k, lane);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) acc[(k * 4 + i) % R] = fmaf(wk, x4[i], acc[(k * 4 + i) % R]);
               }
             } else {
 #pragma unroll
@@ -194,7 +242,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
                 for (int k = 0; k < RX; ++k) accx[cc * RXA + k] = fmaf(wcc, xj[u][k], accx[cc * RXA + k]);
               }
             }
-            if (T::own_writer(lane)) A.edge_e[edge * A.C + myc] = e;
+            if (T::own_writer(lane) && valid) A.edge_e[edge * A.C + myc] = e;
           }
         }
       }
@@ -220,6 +268,20 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
       } else {
         T::store(A.partial + static_cast<int64_t>(it.slot) * A.pwidth + off, acc, lane, A.D);
       }
+    } else if (SHV) {
+      // agg[i, c, :] = acc / (sum w [+ sum w*mask: SAGE's detached "row sum + 1"])
+      if (it.slot < 0) {
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const float den = T::from_owner(ws, k, lane) + (A.plain ? 0.0f : T::from_owner(wms, k, lane));
+          const float inv = den > 0.0f ? 1.0f / den : 0.0f;
+#pragma unroll
+          for (int r = k * RPC; r < (k + 1) * RPC; ++r) acc[r] *= inv;
+        }
+        T::store(A.hpre + srow * A.C * A.D + off, acc, lane, A.D);
+      } else {
+        T::store(A.partial + static_cast<int64_t>(it.slot) * A.pwidth + off, acc, lane, A.D);
+      }
     } else {
       // SAGE: neigh = agg / (rowsum(alpha_drop) + 1) = acc / (sum w*mask + sum w); plain: acc / sum w
 #pragma unroll
@@ -235,7 +297,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
       }
     }
     if (T::own_writer(lane)) {
-      const int aggw = RX == 0 ? A.C * A.D : A.C * A.F;
+      const int aggw = RX <= 0 ? A.C * A.D : A.C * A.F;
       float* st = it.slot < 0 ? A.stats + srow * 2 * A.C : A.partial + static_cast<int64_t>(it.slot) * A.pwidth + aggw;
       st[myc] = ws;
       st[A.C + myc] = wms;
@@ -294,25 +356,37 @@ __global__ void k_combine_rows(const SplitRow* split, int64_t n_split, const flo
 // d logit = alpha (d alpha - t) * s(1-s) [+ g_edge_e]; accumulates dP_i (registers) and da
 // (registers, flushed with vector atomics once per warp).
 template <class T, int ATT, int RX, int U>
-__global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArgs A) {
+__global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int RXA = RX > 0 ? RX : 1, NACC = RX > 0 ? CPW * RX : 1;
-  constexpr int PF = (T::kVec && RX == 0) ? EDIS_PF : 0;
-  const uint64_t pol_hot = A.hot_min <= 3 ? l2_policy_evict_last() : l2_policy_evict_normal();
-  const uint64_t pol_cold = A.hot_min <= 3 ? l2_policy_evict_first() : l2_policy_evict_normal();
-  auto prefetch_src = [&](const LayerArgs& a, int raw, int off) {
-    // this lane's edge: pull the source row's score part and value part (R*128 bytes each) into L2
+  constexpr bool SHV = RX < 0;          // shared operand in the 128-bit layout (F == D)
+  constexpr int PF = (T::kVec && RX <= 0) ? EDIS_PF : 0;
+  // whole-warp L2 prefetch of the edge PF steps ahead, one 128-byte line per lane (see the forward)
+  constexpr int QL = ATT == 2 ? R : 0;
+  auto prefetch_src = [&](int raw, int off, int lane) {
     const int64_t j = raw & kIdMask;
-    const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(a.hot_min) ? pol_hot : pol_cold;
-    if (ATT == 2) prefetch_l2_bulk_hint(a.Q + j * a.ldq + off, R * 128, pol);
-    prefetch_l2_bulk_hint(a.V + j * a.ldv + off, R * 128, pol);
+    const int vl = lane - QL;
+    const float* pp = nullptr;
+    if (lane < QL) pp = A.Q + j * A.ldq + off + lane * 32;
+    else if (SHV ? vl * 32 < A.D : vl < R) pp = A.V + j * A.ldv + (SHV ? 0 : off) + vl * 32;
+    if (pp) {
+      if (is_hot(raw, A.hot_min)) prefetch_l2_line<true>(pp); else prefetch_l2_line<false>(pp);
+    }
   };
   constexpr int SBPL = (R + 7) / 8;   // sign bytes per lane per edge
   const int lane = threadIdx.x & 31;
+  const int xoff = (lane % T::LPCV) * 4;   // SHV: this lane's float4 of the shared operand
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  float da[R];
-  zero<T>(da);
+  // att 3: this warp's running da lives in shared memory (touched once per ROW), not in registers
+  __shared__ float s_da[ATT == 3 ? 8 * 32 * R : 1];
+  float* my_da = s_da + (ATT == 3 ? (threadIdx.x >> 5) * 32 * R + lane : 0);
+  auto flush_da = [&](int g) {
+    float da[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) da[r] = my_da[r * 32];
+    T::atomic_add(A.ga + g * CPW * A.D, da, lane, A.D);
+  };
   int da_grp = -1;
   const int CD = A.C * A.D;
   for (; unit < A.n_units; unit += nwarps) {
@@ -322,8 +396,9 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
     const int c0 = grp * CPW;
     const int off = c0 * A.D;
     if (ATT == 3 && grp != da_grp) {
-      if (da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
-      zero<T>(da);
+      if (da_grp >= 0) flush_da(da_grp);
+#pragma unroll
+      for (int r = 0; r < R; ++r) my_da[r * 32] = 0.0f;
       da_grp = grp;
     }
     const int myc = c0 + T::own_ch(lane);
@@ -350,6 +425,26 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
       }
       if (first_chunk) T::store(A.gh + rowoff, dh, lane, A.D);
       tc = T::reduce_own(tpart, lane);
+    } else if (SHV) {
+      // shared operand: gh = g_agg / div (div detached; plain mean: 1), t = <g_agg, agg>
+      const float wmsv = __ldg(A.stats + srow * 2 * A.C + A.C + myc);
+      const float den = wsum + wmsv;
+      const float rdiv_own = A.plain ? 1.0f : (den > 0.0f ? wsum / den : 0.0f);
+      float go[R], ng[R], tpart[NCH];
+      T::load(go, A.g_out + rowoff, lane, A.D);
+      T::load(ng, A.hpre + rowoff, lane, A.D);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) {
+        tpart[k] = 0.0f;
+        const float rdiv = T::from_owner(rdiv_own, k, lane);
+#pragma unroll
+        for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+          dh[r] = go[r] * rdiv;
+          tpart[k] = fmaf(go[r], ng[r], tpart[k]);
+        }
+      }
+      if (first_chunk) T::store(A.gh + rowoff, dh, lane, A.D);
+      tc = T::reduce_own(tpart, lane);
     } else {
       // SAGE: div = rowsum(alpha_drop) + 1 = (sum w*mask + sum w) / sum w, detached (layers.py:103)
       const float wmsv = __ldg(A.stats + srow * 2 * A.C + A.C + myc);
@@ -373,54 +468,78 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
       }
     }
 
-    float pr[R], ar[R], dP[R], dsd = 0.0f;
-    if (ATT >= 2) T::load(pr, A.P + srow * A.ldp + off, lane, A.D);
-    if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
+    // att 3: dP = 0.01 * (sum of all d logit) + 0.99 * (sum over the edges with z > 0): the second
+    // sum is a predicated add per element, the first one add per channel slot
+    float dP[R], dsum[NCH], dsd = 0.0f;
     zero<T>(dP);
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) dsum[k] = 0.0f;
 
     for (int eb = it.beg; eb < it.end; eb += 32) {
       const int cnt = min(32, it.end - eb);
       const int myj = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
-      if (PF > 0 && lane < cnt && lane < PF) prefetch_src(A, myj, off);
+      if (PF > 0) {
+#pragma unroll
+        for (int pq = 0; pq < PF; ++pq)
+          if (pq < cnt) prefetch_src(__shfl_sync(FULL, myj, pq), off, lane);
+      }
       for (int t = 0; t < cnt; t += U) {
         if (PF > 0) {
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            if (lane == t + u + PF && lane < cnt) prefetch_src(A, myj, off);
+            if (t + u + PF < cnt) prefetch_src(__shfl_sync(FULL, myj, t + u + PF), off, lane);
         }
-        float q[ATT == 2 ? U : 1][R], h[U][R], ev[U], gx[U], xj[U][RXA];
+        float q[ATT == 2 ? U : 1][R], h[RX == 0 ? U : 1][R], ev[U], gx[U], xj[U][RXA];
+        float4 hx[SHV ? U : 1];
         unsigned sg[U];
+        // a short tail re-reads the last edge of the block with d logit forced to 0 (no guards)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t + u < cnt) {
-            const int raw = __shfl_sync(FULL, myj, t + u);
-            const int64_t j = raw & kIdMask;
-            const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(A.hot_min) ? pol_hot : pol_cold;
-            const int64_t edge = eb + t + u;
-            if (ATT == 2) T::load_hint(q[u], A.Q + j * A.ldq + off, lane, A.D, pol);
-            if (ATT == 3) {
-              // the forward's sign record of P_i + Q_j replaces the gather of Q_j (2 KB -> 64 B per edge)
-              const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
-              sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
-                                : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
-            }
-            if (RX == 0) T::load_hint(h[u], A.V + j * A.ldv + off, lane, A.D, pol);
-            else load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
-            ev[u] = __ldg(A.edge_e + edge * A.C + myc);
-            gx[u] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + myc) : 0.0f;
+          const int raw = __shfl_sync(FULL, myj, min(t + u, cnt - 1));
+          const int64_t j = raw & kIdMask;
+          const int64_t edge = eb + min(t + u, cnt - 1);
+          const float* qp = A.Q + j * A.ldq + off;
+          const float* vp = A.V + j * A.ldv + (SHV ? xoff : off);
+          auto go = [&](auto hot) {
+            constexpr bool H = decltype(hot)::value;
+            if (ATT == 2) T::template load_pol<H>(q[ATT == 2 ? u : 0], qp, lane, A.D);
+            if (RX == 0) T::template load_pol<H>(h[RX == 0 ? u : 0], vp, lane, A.D);
+            else if (SHV) hx[SHV ? u : 0] = ldg4_pol<H>(vp);
+          };
+          if (is_hot(raw, A.hot_min)) go(std::true_type{}); else go(std::false_type{});
+          if (ATT == 3) {
+            // the forward's sign record of P_i + Q_j replaces the gather of Q_j (2 KB -> 64 B per edge)
+            const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
+            sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
+                              : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
           }
+          if (RX > 0) load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
+          ev[u] = __ldg(A.edge_e + edge * A.C + myc);
+          gx[u] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + myc) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t + u < cnt) {
-            const int64_t edge = eb + t + u;
+          const bool valid = U == 1 || t + u < cnt;
+          {
+            const int64_t edge = eb + min(t + u, cnt - 1);
             float gdot = 0.0f;
             if (RX == 0) {
               float gpart[NCH];
 #pragma unroll
               for (int k = 0; k < NCH; ++k) gpart[k] = 0.0f;
 #pragma unroll
-              for (int r = 0; r < R; ++r) gpart[r / RPC] = fmaf(dh[r], h[u][r], gpart[r / RPC]);
+              for (int r = 0; r < R; ++r) gpart[r / RPC] = fmaf(dh[r], h[RX == 0 ? u : 0][r], gpart[r / RPC]);
+              gdot = T::reduce_own(gpart, lane);
+            } else if (SHV) {
+              const float4 hv = hx[SHV ? u : 0];
+              const float x4[4] = {hv.x, hv.y, hv.z, hv.w};
+              float gpart[NCH];
+#pragma unroll
+              for (int k = 0; k < NCH; ++k) {
+                gpart[k] = 0.0f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) gpart[k] = fmaf(dh[(k * 4 + i) % R], x4[i], gpart[k]);
+              }
               gdot = T::reduce_own(gpart, lane);
             } else {
 #pragma unroll
@@ -432,12 +551,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
                 if (T::own_ch(lane) == cc) gdot = gp;
               }
             }
-            const float s = sigmoidf_fast(ev[u]);
-            const float alpha = __expf(s) * inv;
+            const float s = sigmoid_mufu(ev[u]);
+            const float alpha = exp_mufu(s) * inv;
             const float ms = A.training ? keep_scale(A.seed, edge * A.C + myc, A.p, A.inv_keep) : 1.0f;
             const float ds = alpha * (gdot * ms - tc);
-            const float de = fmaf(ds, s * (1.0f - s), gx[u]);
-            if (T::own_writer(lane)) {
+            const float de = valid ? fmaf(ds, s * (1.0f - s), gx[u]) : 0.0f;
+            if (T::own_writer(lane) && valid) {
               A.edge_rec[edge * 2 * A.C + myc] = alpha * ms;
               A.edge_rec[edge * 2 * A.C + A.C + myc] = de;
             }
@@ -446,12 +565,15 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
 #pragma unroll
               for (int k = 0; k < NCH; ++k) {
                 const float d = T::from_owner(de, k, lane);
-                const float d001 = 0.01f * d;
+                if (ATT == 3) dsum[k] += d;
 #pragma unroll
                 for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
-                  // att 3: dP accumulates U = sum_j de_ij lrelu'(z_ijd); scaled by a once per row
-                  if (ATT == 3) dP[r] += ((sg[u] >> r) & 1u) ? d : d001;
-                  else dP[r] = fmaf(d, q[ATT == 2 ? u : 0][r], dP[r]);
+                  // att 3: dP accumulates the z > 0 part of U = sum_j de_ij lrelu'(z_ijd)
+                  if (ATT == 3) {
+                    dP[r] = fmaf(sign_pos_f<R>(sg[u], r), d, dP[r]);
+                  } else {
+                    dP[r] = fmaf(d, q[ATT == 2 ? u : 0][r], dP[r]);
+                  }
                 }
               }
             }
@@ -461,11 +583,15 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
     }
     if (ATT == 3) {
       // lrelu(z) = lrelu'(z) z  =>  da_d = sum_i P_i[d] U_i[d] + sum_j Q_j[d] U'_j[d]: per ROW, not per
-      // edge (the source half is added by the src pass)
+      // edge (the source half is added by the src pass).  P_i and a are only needed here.
+      float pr[R], ar[R];
+      T::load(pr, A.P + srow * A.ldp + off, lane, A.D);
+      T::load(ar, A.a + off, lane, A.D);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        da[r] = fmaf(pr[r], dP[r], da[r]);
-        dP[r] *= ar[r];
+        dP[r] = fmaf(0.99f, dP[r], 0.01f * dsum[r / RPC]);     // U_i = sum_j de_ij lrelu'(z_ijd)
+        my_da[r * 32] = fmaf(pr[r], dP[r], my_da[r * 32]);
+        dP[r] *= ar[r];                                        // scaled by a once per row
       }
     }
     if (it.slot < 0) {
@@ -477,32 +603,45 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_dst(const LayerArg
       if (ATT == 1 && T::own_writer(lane)) pb[myc] = dsd;
     }
   }
-  if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
+  if (ATT == 3 && da_grp >= 0) flush_da(da_grp);
 }
 
 // ------------------------------------------------------------------ backward, source pass
 // Per source row j over its out-edges (CSC): dV_j = sum_i alpha_drop_ij gh_i (HASV),
 // dQ_j = sum_i d logit_ij * d e_ij / d Q_j.  Pull: gathers gh_i (and, for att 2, P_i), no atomics
-// on node tensors.  att 3 reads the 1-bit-per-element sign record of the dst pass instead of P_i.
-template <class T, int ATT, bool HASV, int U>
+// on node tensors.  att 3 reads the forward's 1-bit-per-element sign record instead of P_i.
+// HASV: 0 = score side only; 1 = per-channel operand (dV_j[C*D]); 2 = shared operand in the 128-bit
+// layout (F == D, one channel group): dX_j[F] = sum_i sum_c alpha_drop_ij^c gh_i^c, summed over the
+// lane's channel slots in registers and over the warp's channel groups with shuffles once per row.
+template <class T, int ATT, int HASV, int U>
 __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC, CPW = T::CPW;
   constexpr int SBPL = (R + 7) / 8;
   constexpr int PF = T::kVec ? EDIS_PF_SRC : 0;
-  const uint64_t pol_hot = A.hot_min <= 3 ? l2_policy_evict_last() : l2_policy_evict_normal();
-  const uint64_t pol_cold = A.hot_min <= 3 ? l2_policy_evict_first() : l2_policy_evict_normal();
-  auto prefetch_dst = [&](const LayerArgs& a, int raw, int off) {
+  constexpr int QL = ATT == 2 ? R : 0;
+  auto prefetch_dst = [&](int raw, int off, int lane) {
     const int64_t i = raw & kIdMask;
-    const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(a.hot_min) ? pol_hot : pol_cold;
-    if (ATT == 2) prefetch_l2_bulk_hint(a.P + i * a.ldp + off, R * 128, pol);
-    if (HASV) prefetch_l2_bulk_hint(a.gh + i * a.C * a.D + off, R * 128, pol);
+    const int vl = lane - QL;
+    const float* pp = nullptr;
+    if (lane < QL) pp = A.P + i * A.ldp + off + lane * 32;
+    else if (HASV && vl < R) pp = A.gh + i * A.C * A.D + off + vl * 32;
+    if (pp) {
+      if (is_hot(raw, A.hot_min)) prefetch_l2_line<true>(pp); else prefetch_l2_line<false>(pp);
+    }
   };
   const int lane = threadIdx.x & 31;
   const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
   int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int CD = A.C * A.D;
-  float da[R];
-  zero<T>(da);
+  // att 3: this warp's running da lives in shared memory (touched once per ROW), not in registers
+  __shared__ float s_da[ATT == 3 ? 8 * 32 * R : 1];
+  float* my_da = s_da + (ATT == 3 ? (threadIdx.x >> 5) * 32 * R + lane : 0);
+  auto flush_da = [&](int g) {
+    float da[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) da[r] = my_da[r * 32];
+    T::atomic_add(A.ga + g * CPW * A.D, da, lane, A.D);
+  };
   int da_grp = -1;
   for (; unit < A.n_units; unit += nwarps) {
     const int64_t item_id = unit / A.G;
@@ -511,14 +650,17 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
     const int c0 = grp * CPW;
     const int off = c0 * A.D;
     if (ATT == 3 && grp != da_grp) {
-      if (da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
-      zero<T>(da);
+      if (da_grp >= 0) flush_da(da_grp);
+#pragma unroll
+      for (int r = 0; r < R; ++r) my_da[r * 32] = 0.0f;
       da_grp = grp;
     }
     int cidx[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
-    float accV[R], accQ[R], dss[NCH];
+    // att 3: accQ holds the z > 0 part (predicated adds), dss the sum of all d logit per slot:
+    // U'_j = 0.01 * dss + 0.99 * accQ
+    float accV[R], accQ[R], dss[NCH], accX[4] = {0.0f, 0.0f, 0.0f, 0.0f};
     zero<T>(accV);
     zero<T>(accQ);
 #pragma unroll
@@ -527,50 +669,61 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       const int cnt = min(32, it.end - eb);
       const int myi = lane < cnt ? __ldg(A.nbr + eb + lane) : 0;
       const int mye = lane < cnt ? __ldg(A.eid + eb + lane) : 0;
-      if (PF > 0 && lane < cnt && lane < PF) prefetch_dst(A, myi, off);
+      if (PF > 0) {
+#pragma unroll
+        for (int pq = 0; pq < PF; ++pq)
+          if (pq < cnt) prefetch_dst(__shfl_sync(FULL, myi, pq), off, lane);
+      }
       for (int t = 0; t < cnt; t += U) {
         if (PF > 0) {
 #pragma unroll
           for (int u = 0; u < U; ++u)
-            if (lane == t + u + PF && lane < cnt) prefetch_dst(A, myi, off);
+            if (t + u + PF < cnt) prefetch_dst(__shfl_sync(FULL, myi, t + u + PF), off, lane);
         }
-        float pg[U][R], dh[U][R], ad[U][NCH], de[U][NCH];
+        float pg[ATT == 2 ? U : 1][R], dh[HASV ? U : 1][R], ad[U][NCH], de[U][NCH];
         unsigned sg[U];
+        // a short tail re-reads the last edge of the block with its weights forced to 0 (no guards)
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t + u < cnt) {
-            const int raw = __shfl_sync(FULL, myi, t + u);
-            const int64_t i = raw & kIdMask;
-            const uint64_t pol = (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(A.hot_min) ? pol_hot : pol_cold;
-            const int64_t edge = __shfl_sync(FULL, mye, t + u);
-            if (ATT == 2) T::load_hint(pg[u], A.P + i * A.ldp + off, lane, A.D, pol);
-            if (ATT == 3) {
-              const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
-              sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
-                                : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
-            }
-            if (HASV) T::load_hint(dh[u], A.gh + i * CD + off, lane, A.D, pol);
+          const bool valid = U == 1 || t + u < cnt;
+          const int raw = __shfl_sync(FULL, myi, min(t + u, cnt - 1));
+          const int64_t i = raw & kIdMask;
+          const int64_t edge = __shfl_sync(FULL, mye, min(t + u, cnt - 1));
+          const float* pp = A.P + i * A.ldp + off;
+          const float* gp = A.gh + i * CD + off;
+          auto go = [&](auto hot) {
+            constexpr bool H = decltype(hot)::value;
+            if (ATT == 2) T::template load_pol<H>(pg[ATT == 2 ? u : 0], pp, lane, A.D);
+            if (HASV) T::template load_pol<H>(dh[HASV ? u : 0], gp, lane, A.D);
+          };
+          if (is_hot(raw, A.hot_min)) go(std::true_type{}); else go(std::false_type{});
+          if (ATT == 3) {
+            const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
+            sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
+                              : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
+          }
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              if (HASV) ad[u][k] = __ldg(A.edge_rec + edge * 2 * A.C + cidx[k]);
-              de[u][k] = __ldg(A.edge_rec + edge * 2 * A.C + A.C + cidx[k]);
-            }
+          for (int k = 0; k < NCH; ++k) {
+            if (HASV) ad[u][k] = valid ? __ldg(A.edge_rec + edge * 2 * A.C + cidx[k]) : 0.0f;
+            de[u][k] = valid ? __ldg(A.edge_rec + edge * 2 * A.C + A.C + cidx[k]) : 0.0f;
           }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          if (t + u < cnt) {
 #pragma unroll
-            for (int k = 0; k < NCH; ++k) {
-              const float d = de[u][k], d001 = 0.01f * d;
+          for (int k = 0; k < NCH; ++k) {
+            const float d = de[u][k];
 #pragma unroll
-              for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
-                if (HASV) accV[r] = fmaf(ad[u][k], dh[u][r], accV[r]);
-                if (ATT == 3) accQ[r] += ((sg[u] >> r) & 1u) ? d : d001;
-                else if (ATT == 2) accQ[r] = fmaf(d, pg[u][r], accQ[r]);
+            for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+              if (HASV == 1) accV[r] = fmaf(ad[u][k], dh[HASV ? u : 0][r], accV[r]);
+              if (HASV == 2) accX[r % 4] = fmaf(ad[u][k], dh[HASV ? u : 0][r], accX[r % 4]);
+              if (ATT == 3) {
+                accQ[r] = fmaf(sign_pos_f<R>(sg[u], r), d, accQ[r]);
+              } else if (ATT == 2) {
+                accQ[r] = fmaf(d, pg[ATT == 2 ? u : 0][r], accQ[r]);
               }
-              if (ATT == 1) dss[k] += d;
             }
+            if (ATT != 2) dss[k] += d;
           }
         }
       }
@@ -581,12 +734,23 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       T::load(ar, A.a + off, lane, A.D);
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        da[r] = fmaf(qr[r], accQ[r], da[r]);   // source half of da (see the dst pass)
+        accQ[r] = fmaf(0.99f, accQ[r], 0.01f * dss[r / RPC]);
+        my_da[r * 32] = fmaf(qr[r], accQ[r], my_da[r * 32]);   // source half of da (see the dst pass)
         accQ[r] *= ar[r];
       }
     }
+    if (HASV == 2) {
+#pragma unroll
+      for (int o = T::LPCV; o < 32; o <<= 1) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) accX[i] += __shfl_xor_sync(FULL, accX[i], o);
+      }
+      float* dst = it.slot < 0 ? A.gV + static_cast<int64_t>(it.row) * A.ldgv
+                               : A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
+      if (lane < T::LPCV) *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(accX[0], accX[1], accX[2], accX[3]);
+    }
     if (it.slot < 0) {
-      if (HASV) T::store(A.gV + static_cast<int64_t>(it.row) * A.ldgv + off, accV, lane, A.D);
+      if (HASV == 1) T::store(A.gV + static_cast<int64_t>(it.row) * A.ldgv + off, accV, lane, A.D);
       if (ATT >= 2) T::store(A.gQ + static_cast<int64_t>(it.row) * A.ldgq + off, accQ, lane, A.D);
       if (ATT == 1 && T::writer(lane)) {
 #pragma unroll
@@ -594,7 +758,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       }
     } else {
       float* pb = A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
-      if (HASV) T::store(pb + off, accV, lane, A.D);
+      if (HASV == 1) T::store(pb + off, accV, lane, A.D);
       if (ATT >= 2) T::store(pb + CD + off, accQ, lane, A.D);
       if (ATT == 1 && T::writer(lane)) {
 #pragma unroll
@@ -602,7 +766,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
       }
     }
   }
-  if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + da_grp * CPW * A.D, da, lane, A.D);
+  if (ATT == 3 && da_grp >= 0) flush_da(da_grp);
 }
 
 // SAGE: gX_j = sum_i sum_c alpha_drop_ij^c gh_i^c.  One warp per source-row chunk, all channels.
@@ -663,8 +827,13 @@ static int launch_pass(Pass pass, const edis_graph* g, LayerArgs A, cudaStream_t
     constexpr int UB = (ATT == 3 && RX == 0 && T::kVec && T::KV == 4) ? EDIS_UB_KV4 : U;
     return launch_persistent(&k_disga_bwd_dst<T, ATT, RX, UB>, g, A, st);
   }
-  if (RX == 0) return launch_persistent(&k_disga_bwd_src<T, ATT, true, U>, g, A, st);
-  return launch_persistent(&k_disga_bwd_src<T, ATT, false, 4>, g, A, st);
+  constexpr int US = (T::kVec && T::KV == 4) ? EDIS_USRC_KV4 : U;
+  if (RX == 0) return launch_persistent(&k_disga_bwd_src<T, ATT, 1, US>, g, A, st);
+  if (RX < 0) {
+    if (A.gV) return launch_persistent(&k_disga_bwd_src<T, ATT, 2, US>, g, A, st);
+    return launch_persistent(&k_disga_bwd_src<T, ATT, 0, US>, g, A, st);
+  }
+  return launch_persistent(&k_disga_bwd_src<T, ATT, 0, 4>, g, A, st);
 }
 
 template <class T, int RX, int U>
@@ -714,8 +883,19 @@ static int launch_sage_rx(Pass pass, const edis_graph* g, const LayerArgs& A, in
   return EDIS_ERR_UNSUPPORTED;
 }
 
+// Shared operand on the 128-bit layouts: F == D == 64 and all channels in one warp (C = 2, 4, 8).
+static bool sage_shared_vec(int C, int D, int F) {
+  static const int on = env_int("EDIS_SHV", 1);
+  return on && F == D && D == 64 && (C == 2 || C == 4 || C == 8);
+}
+
 static int launch_sage(Pass pass, const edis_graph* g, const LayerArgs& A, int att, cudaStream_t st) {
   const int C = A.C, D = A.D;
+  if (sage_shared_vec(C, D, A.F)) {
+    if (C == 8) return launch_att<VecT<4, 16>, -1, EDIS_US_KV4>(pass, g, A, att, st);
+    if (C == 4) return launch_att<VecT<2, 16>, -1, 2>(pass, g, A, att, st);
+    return launch_att<VecT<1, 16>, -1, 4>(pass, g, A, att, st);
+  }
   if (D == 64 && C % 8 == 0) return launch_sage_rx<VecT<4, 16>>(pass, g, A, att, st);
   if (D == 64 && C % 4 == 0) return launch_sage_rx<VecT<2, 16>>(pass, g, A, att, st);
   if (D == 64 && C % 2 == 0) return launch_sage_rx<VecT<1, 16>>(pass, g, A, att, st);
@@ -792,6 +972,11 @@ static int bwd_score_src(const edis_graph* g, const edis_layer_desc* d, LayerArg
     const int seg = d->att == 1 ? d->C : CD;
     k_combine_rows<<<nblk(g->src.n_split * seg), 256, 0, st>>>(g->src.split, g->src.n_split, A.partial,
                                                               A.pwidth, CD, seg, gQ, A.ldgq);
+    if (sage && gV && sage_shared_vec(d->C, d->D, d->Dv)) {
+      // fused dX of the 128-bit shared-operand path: its partials sit at the head of each slot
+      k_combine_rows<<<nblk(g->src.n_split * d->Dv), 256, 0, st>>>(g->src.split, g->src.n_split, A.partial,
+                                                                  A.pwidth, 0, d->Dv, gV, d->Dv);
+    }
     EDIS_CUDA(cudaGetLastError());
   }
   return EDIS_OK;
@@ -804,6 +989,10 @@ using namespace edis;
 extern "C" int64_t edis_disga_rec_bytes(const edis_graph* g, const edis_layer_desc* d) {
   if (!g || !d || d->C < 1) return EDIS_ERR_ARG;
   return rec_total_bytes(g, d);
+}
+
+extern "C" int edis_disga_sage_fused_gx(const edis_layer_desc* d) {
+  return d && sage_shared_vec(d->C, d->D, d->Dv) ? 1 : 0;
 }
 
 extern "C" int64_t edis_disga_sign_bytes(const edis_graph* g, const edis_layer_desc* d) {
@@ -921,6 +1110,8 @@ extern "C" int edis_disga_sage_fwd(const edis_graph* g, const edis_layer_desc* d
   EDIS_CHECK_ARG(d->att != 3 || a, "edis_disga_sage_fwd: att=3 needs a[C,D]");
   EDIS_CHECK_ARG(d->att == 1 || d->D % 4 != 0 || (vec_ok(P, ldp) && vec_ok(Q, ldq)),
                  "edis_disga_sage_fwd: score operands must be 16-byte aligned with ld %% 4 == 0");
+  EDIS_CHECK_ARG(!sage_shared_vec(d->C, d->D, d->Dv) || (vec_ok(X, ldx) && vec_ok(neigh, 4)),
+                 "edis_disga_sage_fwd: X / neigh must be 16-byte aligned with ld %% 4 == 0");
   const int64_t pw = static_cast<int64_t>(d->C) * d->Dv + 2 * d->C;
   if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_sage_fwd"))) return rc;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -956,6 +1147,9 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
   EDIS_CHECK_ARG(d->Dv >= 1 && d->Dv <= 256, "edis_disga_sage_bwd: F=%d (Dv) must be in [1, 256]", d->Dv);
   EDIS_CHECK_ARG(d->att != 3 || (a && ga), "edis_disga_sage_bwd: att=3 needs a and ga");
   EDIS_CHECK_ARG(d->att != 3 || esign, "edis_disga_sage_bwd: att=3 needs the forward's sign record (esign)");
+  EDIS_CHECK_ARG(!sage_shared_vec(d->C, d->D, d->Dv) ||
+                     (vec_ok(X, ldx) && vec_ok(neigh, 4) && vec_ok(g_neigh, 4) && vec_ok(gh, 4) && vec_ok(gX, 4)),
+                 "edis_disga_sage_bwd: node tensors must be 16-byte aligned with ld %% 4 == 0");
   const int CD = d->C * d->D;
   const int64_t pw = 2 * static_cast<int64_t>(CD) + 2 * d->C + d->Dv;
   if ((rc = check_ws(g, pw, workspace, workspace_bytes, "edis_disga_sage_bwd"))) return rc;
@@ -980,11 +1174,14 @@ extern "C" int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d
       EDIS_CUDA(cudaGetLastError());
     }
   }
+  const bool shv = sage_shared_vec(d->C, d->D, d->Dv);
+  if (!need_gx) A.gV = nullptr;
   if (!ph || (ph & EDIS_FLAG_PHASE_SRC)) {
-    rc = bwd_score_src(g, d, A, true, gQ, nullptr, st);
+    // 128-bit shared-operand path: the source pass also produces gX (no separate gX kernel)
+    rc = bwd_score_src(g, d, A, true, gQ, shv ? A.gV : nullptr, st);
     if (rc) return rc;
   }
-  if (!need_gx || (ph && !(ph & EDIS_FLAG_PHASE_GX))) return EDIS_OK;
+  if (!need_gx || shv || (ph && !(ph & EDIS_FLAG_PHASE_GX))) return EDIS_OK;
   // gX: one warp per source-row chunk, all channels
   A.nbr = g->cscrow;
   A.eid = g->csceid;

@@ -77,6 +77,21 @@ __device__ __forceinline__ float4 ldg4(const float* p) {
 __device__ __forceinline__ float sigmoidf_fast(float x) {
   return __fdividef(1.0f, 1.0f + __expf(-x));
 }
+// Layer kernels: sigmoid and exp(sigmoid) straight on the MUFU units (ex2.approx / rcp.approx with
+// flush-to-zero, no range fix-ups: 2^-22 relative).  Forward and backward use the SAME functions, so
+// the softmax weights recomputed in the backward are bit-identical to the forward's row sums.
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float rcp_fast(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float sigmoid_mufu(float e) { return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * e)); }
+__device__ __forceinline__ float exp_mufu(float s) { return ex2_fast(1.4426950408889634f * s); }
 __device__ __forceinline__ float lrelu01(float z) { return fmaxf(z, 0.01f * z); }
 
 // Counter-based dropout mask: murmur3-style finaliser over (seed, element index).  Train-mode
@@ -115,31 +130,56 @@ __device__ __forceinline__ void prefetch_l2_bulk(const void* p, unsigned bytes) 
 // with the streaming rows under plain LRU.
 constexpr int kHeatShift = 30;
 constexpr int kIdMask = (1 << kHeatShift) - 1;
-__device__ __forceinline__ uint64_t l2_policy_evict_last() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_first() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ uint64_t l2_policy_evict_normal() {
-  uint64_t p;
-  asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(p));
-  return p;
-}
-__device__ __forceinline__ float4 ldg4_hint(const float* ptr, uint64_t pol) {
+// Policy words of createpolicy.fractional.L2::evict_{first,last} with fraction 1.0, passed as
+// IMMEDIATES: the cache-hint operand of ld / cp.async.bulk.prefetch must be warp-uniform, and a
+// policy held in an ordinary register makes the compiler wrap every hinted access in a
+// per-distinct-value loop (R2UR + BRA.U.ANY).  Hot / cold is therefore a BRANCH on the (warp-
+// uniform) heat bits with a constant policy on either side.
+constexpr uint64_t kPolEvictFirst = 0x12F0000000000000ull;
+constexpr uint64_t kPolEvictLast = 0x14F0000000000000ull;
+// cold (non-hub) gathered rows: 1 = evict_first hint, 0 = plain loads
+#ifndef EDIS_COLD_HINT
+#define EDIS_COLD_HINT 1
+#endif
+template <bool HOT>
+__device__ __forceinline__ float4 ldg4_pol(const float* ptr) {
+  if (!HOT && !EDIS_COLD_HINT) return __ldg(reinterpret_cast<const float4*>(ptr));
   float4 v;
   asm volatile("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-               : "l"(ptr), "l"(pol));
+               : "l"(ptr), "l"(HOT ? kPolEvictLast : kPolEvictFirst));
   return v;
 }
-__device__ __forceinline__ void prefetch_l2_bulk_hint(const void* p, unsigned bytes, uint64_t pol) {
-  asm volatile("cp.async.bulk.prefetch.L2.global.L2::cache_hint [%0], %1, %2;" ::"l"(p), "r"(bytes), "l"(pol)
-               : "memory");
+// Per-thread L2 prefetch of the 128-byte line at p.  (cp.async.bulk.prefetch runs on the uniform
+// datapath: issued for a per-lane address the compiler serialises it over the lanes with an
+// R2UR / BRA.U.ANY loop, ~12 instructions per call; this one is a single LSU instruction for 32
+// different lines.)
+template <bool HOT>
+__device__ __forceinline__ void prefetch_l2_line(const void* p) {
+  if (HOT) asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(p));
+  else asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+__device__ __forceinline__ bool is_hot(int raw, int hot_min) {
+  return (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(hot_min);
+}
+// att-3 sign record: for each edge one bit per element of z = P_i + Q_j, bit set <=> z > 0.
+// The forward works on w = (-P_i) - Q_j = -z (negations are free operand modifiers) and pushes the
+// SIGN BIT of w into the record with one funnel shift per element, so element r of R ends up at bit
+// R-1-r.  (z == +0 from two +0 operands reads as positive; everything else, incl. exact cancellation
+// and -0, matches z > 0.  Such an edge carries no gradient to W in either case: x_i = x_j = 0.)
+__device__ __forceinline__ unsigned sign_push(unsigned mask, float w) {
+  return __funnelshift_l(__float_as_uint(w), mask, 1);
+}
+template <int R>
+__device__ __forceinline__ bool sign_pos(unsigned mask, int r) { return (mask & (1u << (R - 1 - r))) != 0u; }
+// 1.0f if element r is positive, else 0.0f -- integer arithmetic only (AND + multiply by the constant
+// that moves the bit onto 0x3f800000), no predicate registers: 16 of them live at once is more
+// than ptxas can allocate in the whole-row kernels.
+template <int R>
+__device__ __forceinline__ float sign_pos_f(unsigned mask, int r) {
+  static_assert(R <= 24, "sign record wider than the float-one trick supports");
+  const int b = R - 1 - r;
+  return __uint_as_float((mask & (1u << b)) * (0x3f800000u >> b));
 }
 
 int launch_grid(const void* kernel, int block, size_t smem, int sm_count);

@@ -11,7 +11,7 @@ constexpr unsigned FULL = 0xffffffffu;
 // the float4 at float offset (k*32 + lane)*4 from the group's first column.
 template <int KV_, int LPC_>
 struct VecT {
-  static constexpr int KV = KV_, LPC = LPC_;
+  static constexpr int KV = KV_, LPC = LPC_, LPCV = LPC_;
   static constexpr int NCH = KV;      // channel slots per lane
   static constexpr int RPC = 4;       // registers per channel slot
   static constexpr int R = 4 * KV;
@@ -74,11 +74,11 @@ struct VecT {
       r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
     }
   }
-  __device__ static __forceinline__ void load_hint(float (&r)[R], const float* base, int lane, int,
-                                                   uint64_t pol) {
+  template <bool HOT>
+  __device__ static __forceinline__ void load_pol(float (&r)[R], const float* base, int lane, int) {
 #pragma unroll
     for (int k = 0; k < KV; ++k) {
-      const float4 v = ldg4_hint(base + (k * 32 + lane) * 4, pol);
+      const float4 v = ldg4_pol<HOT>(base + (k * 32 + lane) * 4);
       r[4 * k] = v.x; r[4 * k + 1] = v.y; r[4 * k + 2] = v.z; r[4 * k + 3] = v.w;
     }
   }
@@ -98,7 +98,7 @@ struct VecT {
 // ScaT: any D <= 32*ND, one channel per warp, lane-strided scalar accesses.
 template <int ND_>
 struct ScaT {
-  static constexpr int NCH = 1, RPC = ND_, R = ND_, CPW = 1, KV = 0;
+  static constexpr int NCH = 1, RPC = ND_, R = ND_, CPW = 1, KV = 0, LPCV = 1;
   static constexpr bool kVec = false;
   __device__ static __forceinline__ int ch(int, int) { return 0; }
   __device__ static __forceinline__ bool writer(int lane) { return lane == 0; }
@@ -118,7 +118,8 @@ struct ScaT {
 #pragma unroll
     for (int k = 0; k < ND_; ++k) r[k] = (k * 32 + lane < D) ? __ldg(base + k * 32 + lane) : 0.0f;
   }
-  __device__ static __forceinline__ void load_hint(float (&r)[R], const float* base, int lane, int D, uint64_t) {
+  template <bool HOT>
+  __device__ static __forceinline__ void load_pol(float (&r)[R], const float* base, int lane, int D) {
     load(r, base, lane, D);
   }
   __device__ static __forceinline__ void store(float* base, const float (&r)[R], int lane, int D) {

@@ -41,7 +41,7 @@ class KernelTimer:
 
     def __init__(self):
         self.enabled = False
-        self.records = {}     # name -> list of (start_event, end_event)
+        self.records = {}     # name -> list of (start_event, end_event, bytes dict)
         self.launches = 0
 
     def reset(self):
@@ -49,15 +49,53 @@ class KernelTimer:
         self.launches = 0
 
     def durations_ms(self):
-        return {k: [a.elapsed_time(b) for a, b in v] for k, v in self.records.items()}
+        return {k: [a.elapsed_time(b) for a, b, _ in v] for k, v in self.records.items()}
+
+    def bytes(self):
+        return {k: [m for _, _, m in v] for k, v in self.records.items()}
 
 
 TIMER = KernelTimer()
 
 
+def kernel_bytes(kind, n, nc, e, att, C, D, Fin=None, sage=False):
+    """Bytes of one layer kernel launch, fp32: {"alg": ..., "moved": ...}.
+
+    alg   = SURVEY 8(d)'s gather model of the REFERENCE's layer (every gathered row is DRAM traffic):
+            fwd E(score + agg + 4C + 4) + 8CD N; bwd split as dst pass E(score + agg + 4C + 4) + 8CD N
+            and src pass E(score + agg) + 4CD N, with score = 4CD (att 2/3) or 4C (att 1) and
+            agg = 4CD (gnn AT / GCN, whatever plan executes it) or 4F (SAGE).
+    moved = what THIS implementation has to move if nothing hits in L2 (att-3 sign record instead of
+            re-gathering Q_j / P_i in the backward; F floats instead of C*D for a shared operand)."""
+    CD = C * D
+    score = 4 * C if att == 1 else 4 * CD
+    agg_ref = 4 * Fin if sage else 4 * CD                 # the reference layer's aggregated operand
+    agg_own = 4 * CD if Fin is None else 4 * Fin          # what this kernel gathers per edge
+    wout = CD if Fin is None else C * Fin                 # node-tensor width of the aggregate
+    sign = CD // 8 if att == 3 else 0
+    if kind == "fwd":
+        alg = e * (score + agg_ref + 4 * C + 4) + 8 * CD * n
+        moved = e * (score + agg_own + 4 * C + sign + 4) + n * (score + 4 * wout * (1 if Fin else 2) + 8 * C)
+    elif kind == "bwd_dst":
+        alg = e * (score + agg_ref + 4 * C + 4) + 8 * CD * n
+        moved = (e * ((score if att == 2 else 0) + agg_own + 4 * C + 8 * C + sign + 4)
+                 + n * (12 * wout + 2 * score + 8 * C))
+    elif kind == "bwd_src":
+        alg = e * (score + agg_ref) + 4 * CD * n
+        moved = (e * ((score if att == 2 else 0) + 4 * wout + 8 * C + sign + 8)
+                 + nc * (score + (4 * CD if Fin is None else 4 * Fin)))
+    elif kind == "bwd_src_score":                         # lane-strided shared operand: score side only
+        alg = e * score + 4 * CD * n
+        moved = e * ((score if att == 2 else 0) + 8 * C + sign + 8) + nc * score
+    else:                                                 # "bwd_gx": separate dX kernel of that path
+        alg = e * agg_ref
+        moved = e * (4 * wout + 4 * C + 8) + nc * 4 * Fin
+    return {"alg": int(alg), "moved": int(moved)}
+
+
 class _timed:
-    def __init__(self, name, graph, launches):
-        self.name, self.launches = name, launches
+    def __init__(self, name, graph, launches, nbytes=None):
+        self.name, self.launches, self.nbytes = name, launches, nbytes
 
     def __enter__(self):
         if TIMER.enabled:
@@ -69,7 +107,7 @@ class _timed:
     def __exit__(self, *exc):
         if TIMER.enabled:
             self.end.record(torch.cuda.current_stream())
-            TIMER.records.setdefault(self.name, []).append((self.start, self.end))
+            TIMER.records.setdefault(self.name, []).append((self.start, self.end, self.nbytes))
             TIMER.launches += self.launches
         return False
 
@@ -131,7 +169,8 @@ class DisGAFused(torch.autograd.Function):
         ws, nbytes = _workspace(graph, CD + 2 * C, proj)
         d = _desc(att, C, D, training, p, seed)
         esign = _sign_rec(graph, d, proj.device, any(ctx.needs_input_grad))
-        with _timed("disga_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
+        with _timed("disga_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0),
+                    kernel_bytes("fwd", n, graph.n_cols, e, att, C, D)):
             check(lib.edis_disga_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a),
                                      _off(proj, off_v), ld, _ptr(bias), _ptr(out), _ptr(hpre), _ptr(edge_e),
                                      _ptr(stats), _ptr(esign), _ptr(ws), nbytes, _stream()), "edis_disga_fwd")
@@ -182,9 +221,11 @@ class DisGAFused(torch.autograd.Function):
         args = (graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _off(proj, off_v), ld, _ptr(bias),
                 _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_out), _ptr(g_edge_e), gP, ldgp, gQ, ldgq,
                 _ptr(ga), _off(g_proj, off_v), W, _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream())
-        with _timed("disga_bwd_dst", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
+        with _timed("disga_bwd_dst", graph, 1 + (1 if graph.info["dst_slots"] else 0),
+                    kernel_bytes("bwd_dst", n, nc, e, att, C, D)):
             check(lib.edis_disga_bwd_dst(*args), "edis_disga_bwd_dst")
-        with _timed("disga_bwd_src", graph, 1 + (2 if graph.info["src_slots"] else 0)):
+        with _timed("disga_bwd_src", graph, 1 + (2 if graph.info["src_slots"] else 0),
+                    kernel_bytes("bwd_src", n, nc, e, att, C, D)):
             check(lib.edis_disga_bwd_src(*args), "edis_disga_bwd_src")
         if gq_sep is not None:
             g_proj[:, off_p:off_p + CD] += gq_sep
@@ -227,12 +268,13 @@ class SageFused(torch.autograd.Function):
         d.Dv = Fin
         d.flags = (_lib.FLAG_PLAIN_MEAN if plain else 0) | (0 if ctx.needs_input_grad[10] else _lib.FLAG_NO_GX)
         esign = _sign_rec(graph, d, X.device, any(ctx.needs_input_grad))
-        with _timed("disga_sage_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0)):
+        with _timed("disga_sage_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0),
+                    kernel_bytes("fwd", n, graph.n_cols, e, att, C, D, Fin, sage=not plain)):
             check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X), ldx,
                                           _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(ws), nbytes,
                                           _stream()),
                   "edis_disga_sage_fwd")
-        ctx.graph, ctx.d, ctx.offs, ctx.ldx = graph, d, (off_p, off_q), ldx
+        ctx.graph, ctx.d, ctx.offs, ctx.ldx, ctx.plain = graph, d, (off_p, off_q), ldx, bool(plain)
         ctx.has_a = a is not None
         ctx.save_for_backward(proj, sdst, ssrc, a, X, agg, edge_e, stats, esign)
         ctx.set_materialize_grads(False)
@@ -278,13 +320,17 @@ class SageFused(torch.autograd.Function):
         gh = torch.empty(n, C * Fin, dtype=torch.float32, device=dev)
         ws, nbytes = _workspace(graph, 2 * CD + 2 * C + Fin, X)
         base = d.flags
-        phases = [("disga_sage_bwd_dst", _lib.FLAG_PHASE_DST, 1 + (1 if graph.info["dst_slots"] else 0)),
-                  ("disga_sage_bwd_src", _lib.FLAG_PHASE_SRC, 1 + (1 if graph.info["src_slots"] else 0))]
-        if need_gx:
-            phases.append(("disga_sage_bwd_gx", _lib.FLAG_PHASE_GX, 1 + (1 if graph.info["src_slots"] else 0)))
-        for name, bit, nl in phases:
+        fused_gx = bool(lib.edis_disga_sage_fused_gx(ctypes.byref(d)))
+        kb = lambda kind: kernel_bytes(kind, n, nc, e, att, C, D, Fin, sage=not ctx.plain)
+        phases = [("disga_sage_bwd_dst", _lib.FLAG_PHASE_DST, 1 + (1 if graph.info["dst_slots"] else 0), kb("bwd_dst")),
+                  ("disga_sage_bwd_src", _lib.FLAG_PHASE_SRC, 1 + (1 if graph.info["src_slots"] else 0),
+                   kb("bwd_src" if (fused_gx and need_gx) else "bwd_src_score"))]
+        if need_gx and not fused_gx:
+            phases.append(("disga_sage_bwd_gx", _lib.FLAG_PHASE_GX, 1 + (1 if graph.info["src_slots"] else 0),
+                           kb("bwd_gx")))
+        for name, bit, nl, nb in phases:
             d.flags = base | bit
-            with _timed(name, graph, nl):
+            with _timed(name, graph, nl, nb):
                 check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X),
                                               ctx.ldx, _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_agg),
                                               _ptr(g_edge_e), gP, ldgp, gQ, ldgq, _ptr(ga), _ptr(gX),

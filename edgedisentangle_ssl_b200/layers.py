@@ -79,11 +79,15 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
         raise _lib.EdisError("DisGALayer input must be a float32 CUDA tensor; there is no CPU fallback")
     CD = C * D
     # Execution plan for gnn_type AT / GCN.  "proj" (default): project first, gather V_j = (x W)_j per
-    # edge with 128-bit loads.  "agg" (EDIS_AT_PLAN=agg, F <= 256): aggregate the raw input per channel
-    # with the shared-operand kernels and project afterwards -- 5x / 8x fewer gathered bytes for the
-    # aggregated operand at F=100 / 64, but those kernels are issue-bound (lane-strided accumulators,
-    # full-warp reductions per channel) and measured slower on B200 (profiles/r1_sweep4.log).
-    # SAGE always uses the shared-operand kernels.
+    # edge with 128-bit loads (C*D floats per edge).  "agg" (EDIS_AT_PLAN=agg, F <= 256): aggregate the
+    # raw input per channel with the shared-operand kernels and project afterwards,
+    # (sum_j a_ij x_j) W == sum_j a_ij (x_j W): only F floats of the aggregated operand are gathered per
+    # edge, in the forward and in the destination pass of the backward.  Where the shared operand fits
+    # the 128-bit layout (F == D == 64, C in {2, 4, 8}: DISGAT's second layer) its kernels beat the
+    # "proj" ones (B200, config A: fwd 38.7 vs 44 ms, dst pass 27.4 vs 34.6 ms), but they are issue-bound,
+    # not HBM-bound, and the extra per-channel GEMM + ELU passes eat the gain (291 vs 286 ms per step,
+    # profiles/r1_sweep10.log); for other F the operand runs lane-strided and is slower still
+    # (profiles/r1_sweep4_plans.log).  SAGE always uses the shared-operand kernels.
     plan = os.environ.get("EDIS_AT_PLAN") or "proj"
     use_agg = aggregate and (gnn == "SAGE" or plan == "agg")
     a = None

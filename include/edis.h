@@ -197,6 +197,10 @@ int edis_disga_sage_bwd(const edis_graph* g, const edis_layer_desc* d,
                         float* edge_rec, float* gh,
                         void* workspace, int64_t workspace_bytes, void* stream);
 
+/* 1 if this shape runs on the 128-bit shared-operand path (F == D == 64, C in {2,4,8}), whose
+ * source pass (EDIS_FLAG_PHASE_SRC) also produces gX: EDIS_FLAG_PHASE_GX is then a no-op. */
+int edis_disga_sage_fused_gx(const edis_layer_desc* d);
+
 /* ------------------------------------------------------------------ pair scoring (SSL)
  * Logits on arbitrary (i, j) pair lists, all channels [c_lo, c_hi) at once, no [M, .] temps.
  * Replaces layers.py:355-360 / 368-372 / 381-389 (`edge_auxs`).  pi/pj: int64 device arrays.

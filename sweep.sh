@@ -7,9 +7,8 @@ run() { # name, then VAR=val ...
 import sys, json
 d = json.loads(sys.stdin.read())
 k = d['roofline']['kernels']
-print('$name', 'ms/step %.1f' % d['ms_per_step'], 'Medges/s %.1f' % (d['value']/1e6), ' '.join('%s=%.1f(%.0f)' % (a.replace('disga_',''), b['ms_per_step'], b['gbs']) for a, b in k.items()))
+print('$name', 'ms/step %.1f' % d['ms_per_step'], 'Medges/s %.1f' % (d['value']/1e6), ' '.join('%s=%.1f(%.0f/%.0f)' % (a.replace('disga_',''), b['ms_per_step'], b['gbs'], b['moved_gbs']) for a, b in k.items()))
 "
 }
-run ub2 X=1
-run ub1 EDIS_LIB=$PWD/variants/libedis_ub1.so
-run ub4 EDIS_LIB=$PWD/variants/libedis_ub4.so
+run auto X=1
+run proj EDIS_AT_PLAN=proj

@@ -241,6 +241,9 @@ CASES = [
     (120, 700, 2, 13, 7, 0),        # scalar path, D % 4 != 0
     (90, 500, 4, 32, 12, 4),        # VecT<1,8>
     (80, 400, 1, 128, 9, 0),        # VecT<1,32>
+    (260, 2200, 8, 64, 64, 16),     # F == D == 64: shared operand on the 128-bit layout (layer-2 shape), split rows
+    (180, 1400, 4, 64, 64, 0),      # same, VecT<2,16>
+    (150, 1000, 2, 64, 64, 8),      # same, VecT<1,16>
 ]
 
 
