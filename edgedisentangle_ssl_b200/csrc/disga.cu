@@ -208,8 +208,8 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
                 // 1 bit per element of P_i + Q_j, saved for the backward: leaky-relu is piecewise
                 // linear, so neither backward pass needs z itself, only lrelu'(z)
                 const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
-                if (SBPL == 1) A.esign[so] = static_cast<unsigned char>(mask);
-                else *reinterpret_cast<unsigned short*>(A.esign + so) = static_cast<unsigned short>(mask);
+                if (SBPL == 1) st_stream(A.esign + so, static_cast<unsigned char>(mask));
+                else st_stream(reinterpret_cast<unsigned short*>(A.esign + so), static_cast<unsigned short>(mask));
               }
               e = T::reduce_own(part, lane);
             }
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
                 for (int k = 0; k < RX; ++k) accx[cc * RXA + k] = fmaf(wcc, xj[u][k], accx[cc * RXA + k]);
               }
             }
-            if (T::own_writer(lane) && valid) A.edge_e[edge * A.C + myc] = e;
+            if (T::own_writer(lane) && valid) st_stream(A.edge_e + edge * A.C + myc, e);
           }
         }
       }
@@ -510,12 +510,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst(const Laye
           if (ATT == 3) {
             // the forward's sign record of P_i + Q_j replaces the gather of Q_j (2 KB -> 64 B per edge)
             const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
-            sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
-                              : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
+            sg[u] = SBPL == 1 ? static_cast<unsigned>(ld_stream(A.esign + so))
+                              : static_cast<unsigned>(ld_stream(reinterpret_cast<const unsigned short*>(A.esign + so)));
           }
           if (RX > 0) load_x<RX>(xj[u], A.V + j * A.ldv, lane, A.F);
-          ev[u] = __ldg(A.edge_e + edge * A.C + myc);
-          gx[u] = A.g_edge_e ? __ldg(A.g_edge_e + edge * A.C + myc) : 0.0f;
+          ev[u] = ld_stream(A.edge_e + edge * A.C + myc);
+          gx[u] = A.g_edge_e ? ld_stream(A.g_edge_e + edge * A.C + myc) : 0.0f;
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -557,8 +557,8 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst(const Laye
             const float ds = alpha * (gdot * ms - tc);
             const float de = valid ? fmaf(ds, s * (1.0f - s), gx[u]) : 0.0f;
             if (T::own_writer(lane) && valid) {
-              A.edge_rec[edge * 2 * A.C + myc] = alpha * ms;
-              A.edge_rec[edge * 2 * A.C + A.C + myc] = de;
+              st_stream(A.edge_rec + edge * 2 * A.C + myc, alpha * ms);
+              st_stream(A.edge_rec + edge * 2 * A.C + A.C + myc, de);
             }
             if (ATT == 1) dsd += de;
             if (ATT >= 2) {
@@ -699,13 +699,13 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src(const LayerArg
           if (is_hot(raw, A.hot_min)) go(std::true_type{}); else go(std::false_type{});
           if (ATT == 3) {
             const int64_t so = ((edge * A.G + grp) * 32 + lane) * SBPL;
-            sg[u] = SBPL == 1 ? static_cast<unsigned>(__ldg(A.esign + so))
-                              : static_cast<unsigned>(__ldg(reinterpret_cast<const unsigned short*>(A.esign + so)));
+            sg[u] = SBPL == 1 ? static_cast<unsigned>(ld_stream(A.esign + so))
+                              : static_cast<unsigned>(ld_stream(reinterpret_cast<const unsigned short*>(A.esign + so)));
           }
 #pragma unroll
           for (int k = 0; k < NCH; ++k) {
-            if (HASV) ad[u][k] = valid ? __ldg(A.edge_rec + edge * 2 * A.C + cidx[k]) : 0.0f;
-            de[u][k] = valid ? __ldg(A.edge_rec + edge * 2 * A.C + A.C + cidx[k]) : 0.0f;
+            if (HASV) ad[u][k] = valid ? ld_stream(A.edge_rec + edge * 2 * A.C + cidx[k]) : 0.0f;
+            de[u][k] = valid ? ld_stream(A.edge_rec + edge * 2 * A.C + A.C + cidx[k]) : 0.0f;
           }
         }
 #pragma unroll

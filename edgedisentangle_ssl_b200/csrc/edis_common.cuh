@@ -162,6 +162,20 @@ __device__ __forceinline__ void prefetch_l2_line(const void* p) {
 __device__ __forceinline__ bool is_hot(int raw, int hot_min) {
   return (static_cast<unsigned>(raw) >> kHeatShift) >= static_cast<unsigned>(hot_min);
 }
+// Per-edge records (logits, sign bits, (alpha, d logit)) are written once and read once per pass:
+// streaming (evict-first) accesses keep them from displacing the gathered node rows in L2.
+#ifndef EDIS_STREAM_HINT
+#define EDIS_STREAM_HINT 1
+#endif
+template <class V>
+__device__ __forceinline__ void st_stream(V* p, V v) {
+  if (EDIS_STREAM_HINT) __stcs(p, v); else *p = v;
+}
+template <class V>
+__device__ __forceinline__ V ld_stream(const V* p) {
+  return EDIS_STREAM_HINT ? __ldcs(p) : __ldg(p);
+}
+
 // att-3 sign record: for each edge one bit per element of z = P_i + Q_j, bit set <=> z > 0.
 // The forward works on w = (-P_i) - Q_j = -z (negations are free operand modifiers) and pushes the
 // SIGN BIT of w into the record with one funnel shift per element, so element r of R ends up at bit
