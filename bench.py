@@ -143,9 +143,10 @@ def cora_full_epoch_ms():
             "--pre_weight", "1", "1", "1", "--pre_edge", "1", "1", "1", "--sparse", "--att=3",
             "--constrain_layer=0", "--epochs=4", "--gnn_type=AT"]
     out = {}
-    for name, env in (("reference_rng_sampler", {"EDIS_SAMPLER": "exact", "EDIS_HOST_METRICS": "1"}),
-                      ("device_sampler", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "1"}),
-                      ("device_sampler_no_sklearn", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "0"})):
+    for name, env in (("reference_rng_sampler_sklearn", {"EDIS_SAMPLER": "exact", "EDIS_HOST_METRICS": "1"}),
+                      ("device_sampler_sklearn", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "1"}),
+                      ("device_sampler_device_metrics", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "device"}),
+                      ("device_sampler_no_metrics", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "0"})):
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -158,7 +159,10 @@ def cora_full_epoch_ms():
                     os.environ.pop(k, None)
                 else:
                     os.environ[k] = v
-    out["note"] = ("cora_full N=19793 E=146635, synthetic 64-d features (the feature blob is missing from the "
+    out["note"] = ("rows: SSL pair sampler (exact = the reference's CPU RNG stream replayed bit for bit, O(N^2) "
+                   "uniforms per draw; device = same law in O(M) on the GPU) x validation AUC / macro-F1 per CLS "
+                   "step (sklearn on host copies like the reference / computed on the device / dropped).  "
+                   "cora_full N=19793 E=146635, synthetic 64-d features (the feature blob is missing from the "
                    "reference snapshot); epoch 1 (graph build, warm-up) excluded; the reference's CPU path "
                    "took ~49 s per epoch in the survey probe (BASELINE.md)")
     return out
