@@ -77,8 +77,8 @@ SIGNATURES = {
                                     _P, c_int64, _P, _P, _P]),
     "edis_pair_score_bwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,
                                     _P, c_int64, _P, _P, _P, _P, _P, _P]),
-    "edis_ssl_wmse_fwd": (c_int, [c_int64, c_int32, _P, _P, c_int64, _P, _P, c_int64, _P]),
-    "edis_ssl_wmse_bwd": (c_int, [c_int64, c_int32, _P, _P, c_int64, _P, _P, _P]),
+    "edis_ssl_wmse_fwd": (c_int, [c_int64, c_int32, _P, _P, c_int64, c_int64, _P, _P, c_int64, _P]),
+    "edis_ssl_wmse_bwd": (c_int, [c_int64, c_int32, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "edis_nll_const_label_fwd": (c_int, [c_int64, c_int32, _P, c_int32, _P, _P, c_int64, _P]),
     "edis_nll_const_label_bwd": (c_int, [c_int64, c_int32, _P, c_int32, _P, _P, _P]),
     "edis_sp_softmax_fwd": (c_int, [c_int64, c_int64, _P, _P, _P, _P, _P, _P]),

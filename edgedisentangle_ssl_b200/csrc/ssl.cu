@@ -402,9 +402,9 @@ static float neg_weight(int64_t m, int64_t n_pos) {
 }
 
 extern "C" int edis_ssl_wmse_fwd(int64_t m, int32_t cs, const float* scores, const float* target,
-                                 int64_t n_pos, float* loss, void* workspace, int64_t workspace_bytes,
-                                 void* stream) {
-  EDIS_CHECK_ARG(m > 0 && cs > 0 && scores && target && loss, "edis_ssl_wmse_fwd: bad arguments");
+                                 int64_t n_pos, int64_t m_total, float* loss, void* workspace,
+                                 int64_t workspace_bytes, void* stream) {
+  EDIS_CHECK_ARG(m > 0 && cs > 0 && scores && target && loss && m_total >= m, "edis_ssl_wmse_fwd: bad arguments");
   if (!workspace || workspace_bytes < 8) {
     set_error("edis_ssl_wmse_fwd: workspace must hold 8 bytes");
     return EDIS_ERR_WORKSPACE;
@@ -412,17 +412,20 @@ extern "C" int edis_ssl_wmse_fwd(int64_t m, int32_t cs, const float* scores, con
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   double* acc = static_cast<double*>(workspace);
   EDIS_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), st));
-  k_wmse_fwd<<<ngrid(m), 256, 0, st>>>(m, cs, scores, target, neg_weight(m, n_pos), acc);
-  k_finalize_mean<<<1, 1, 0, st>>>(acc, 1.0 / static_cast<double>(m), loss);
+  k_wmse_fwd<<<ngrid(m), 256, 0, st>>>(m, cs, scores, target, neg_weight(m_total, n_pos), acc);
+  k_finalize_mean<<<1, 1, 0, st>>>(acc, 1.0 / static_cast<double>(m_total), loss);
   EDIS_CUDA(cudaGetLastError());
   return EDIS_OK;
 }
 
 extern "C" int edis_ssl_wmse_bwd(int64_t m, int32_t cs, const float* scores, const float* target,
-                                 int64_t n_pos, const float* g_loss, float* g_scores, void* stream) {
-  EDIS_CHECK_ARG(m > 0 && cs > 0 && scores && target && g_loss && g_scores, "edis_ssl_wmse_bwd: bad arguments");
+                                 int64_t n_pos, int64_t m_total, const float* g_loss, float* g_scores,
+                                 void* stream) {
+  EDIS_CHECK_ARG(m > 0 && cs > 0 && scores && target && g_loss && g_scores && m_total >= m,
+                 "edis_ssl_wmse_bwd: bad arguments");
   k_wmse_bwd<<<ngrid(m), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      m, cs, scores, target, neg_weight(m, n_pos), static_cast<float>(1.0 / static_cast<double>(m)), g_loss, g_scores);
+      m, cs, scores, target, neg_weight(m_total, n_pos), static_cast<float>(1.0 / static_cast<double>(m_total)),
+      g_loss, g_scores);
   EDIS_CUDA(cudaGetLastError());
   return EDIS_OK;
 }

@@ -453,7 +453,7 @@ class PairScore(torch.autograd.Function):
         n, m = P.shape[0], pi.numel()
         wdt = d.C if d.att == 1 else d.C * d.D
         gP = torch.zeros(n, wdt, dtype=torch.float32, device=P.device)
-        gQ = torch.zeros(n, wdt, dtype=torch.float32, device=P.device)
+        gQ = torch.zeros(Q.shape[0], wdt, dtype=torch.float32, device=P.device)   # P and Q may differ in rows
         ga = torch.zeros(d.C, d.D, dtype=torch.float32, device=P.device) if d.att == 3 else None
         g_out = g_out.contiguous()
         check(lib.edis_pair_score_bwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
@@ -467,15 +467,18 @@ class SslWmse(torch.autograd.Function):
     weights.  Replaces pretrainer.py:730-737 / 613-627 + utils.adj_mse_loss (utils.py:287-298)."""
 
     @staticmethod
-    def forward(ctx, scores, target, n_pos):
+    def forward(ctx, scores, target, n_pos, m_total=None):
+        """m_total / n_pos: size and positive count of the whole pair set when `scores` is one
+        rank's slice of it (parallel.ssl_pair_loss_partitioned); default m_total = len(scores)."""
         scores = scores.contiguous()
         target = target.contiguous()
         m, cs = scores.shape
+        m_total = m if m_total is None else int(m_total)
         loss = torch.empty(1, dtype=torch.float32, device=scores.device)
         ws = torch.empty(8, dtype=torch.uint8, device=scores.device)
-        check(lib.edis_ssl_wmse_fwd(m, cs, _ptr(scores), _ptr(target), int(n_pos), _ptr(loss), _ptr(ws), 8,
+        check(lib.edis_ssl_wmse_fwd(m, cs, _ptr(scores), _ptr(target), int(n_pos), m_total, _ptr(loss), _ptr(ws), 8,
                                     _stream()), "edis_ssl_wmse_fwd")
-        ctx.n_pos = int(n_pos)
+        ctx.n_pos, ctx.m_total = int(n_pos), m_total
         ctx.save_for_backward(scores, target)
         return loss.reshape(())
 
@@ -485,9 +488,9 @@ class SslWmse(torch.autograd.Function):
         m, cs = scores.shape
         g_scores = torch.empty_like(scores)
         g_loss = g_loss.reshape(1).contiguous().float()
-        check(lib.edis_ssl_wmse_bwd(m, cs, _ptr(scores), _ptr(target), ctx.n_pos, _ptr(g_loss),
+        check(lib.edis_ssl_wmse_bwd(m, cs, _ptr(scores), _ptr(target), ctx.n_pos, ctx.m_total, _ptr(g_loss),
                                     _ptr(g_scores), _stream()), "edis_ssl_wmse_bwd")
-        return g_scores, None, None
+        return g_scores, None, None, None
 
 
 class NllConstLabel(torch.autograd.Function):

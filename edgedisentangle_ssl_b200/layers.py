@@ -152,6 +152,28 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
     return out, edge_e, auxs
 
 
+def pair_operands(chs, x_dst, x_src):
+    """Score-side operands of C channels for pairs whose row side and column side live in two
+    different node tensors (multi-GPU SSL: rows = this rank's nodes, columns = all nodes):
+    P from x_dst, Q from x_src, as `run_channels` builds them from one tensor (layers.py:349-389).
+    Pure torch.  Returns (att, C, D, P, Q, a)."""
+    l0 = chs[0]
+    C, D, Fin, att = len(chs), l0.out_features, l0.in_features, l0.att_type
+    if att == 3:
+        a = torch.cat([l.a.reshape(1, D) for l in chs], 0)
+        P = x_dst @ torch.cat([l.W[:Fin] for l in chs], 1)
+        Q = x_src @ torch.cat([l.W[Fin:] for l in chs], 1)
+        return att, C, D, P, Q, a
+    w = torch.cat([l.W for l in chs], 1)
+    P, Q = x_dst @ w, x_src @ w
+    if att == 1:
+        a_top = torch.cat([l.a[:D].reshape(1, D) for l in chs], 0)
+        a_bot = torch.cat([l.a[D:].reshape(1, D) for l in chs], 0)
+        P = (P.reshape(-1, C, D) * a_top).sum(-1)
+        Q = (Q.reshape(-1, C, D) * a_bot).sum(-1)
+    return att, C, D, P, Q, None
+
+
 class DisGALayer(nn.Module):
     """One disentangled attention channel; drop-in for layers.py:303-511 (sparse branch)."""
 

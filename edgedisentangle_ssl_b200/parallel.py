@@ -143,6 +143,99 @@ def get_em_partitioned(enc, fusers, x_local, part, layer_fn=None):
     return feats
 
 
+class AllGatherRows(torch.autograd.Function):
+    """x_local[n_local, F] -> x_all[n_total, F] in global node order (the ranges are contiguous and
+    rank-ordered).  Backward: every rank holds a partial gradient for ALL rows -> reduce-scatter to
+    the owners.  Ranges may differ in size: rows are padded to the largest one."""
+
+    @staticmethod
+    def forward(ctx, x_local, part):
+        ctx.part = part
+        if part.world == 1:
+            return x_local
+        sizes = np.diff(part.bounds)
+        m = int(sizes.max())
+        pad = x_local.new_zeros(m, x_local.shape[1])
+        pad[:part.n_local] = x_local
+        bufs = [torch.empty_like(pad) for _ in range(part.world)]
+        dist.all_gather(bufs, pad)
+        return torch.cat([b[:int(s)] for b, s in zip(bufs, sizes)], 0)
+
+    @staticmethod
+    def backward(ctx, g_all):
+        part = ctx.part
+        if part.world == 1:
+            return g_all, None
+        if dist.get_backend() == "nccl":
+            sizes = np.diff(part.bounds)
+            m = int(sizes.max())
+            chunks = []
+            for r in range(part.world):
+                c = g_all.new_zeros(m, g_all.shape[1])
+                c[:int(sizes[r])] = g_all[int(part.bounds[r]):int(part.bounds[r + 1])]
+                chunks.append(c)
+            out = torch.empty_like(chunks[0])
+            dist.reduce_scatter(out, chunks)
+            return out[:part.n_local].contiguous(), None
+        g = g_all.contiguous().clone()            # gloo has no reduce_scatter: all-reduce, keep own rows
+        dist.all_reduce(g)
+        return g[part.lo:part.hi].contiguous(), None
+
+
+def ssl_pair_loss_partitioned(enc, fusers, x_local, part, pairs, labels, ranges, n_pos_total, m_total,
+                              constrain_layer=0, layer_fn=None, pair_fn=None, loss_fn=None):
+    """SupEdge / DisEdge loss (pretrainer.py:709-763, 578-641) over a destination-range partition.
+
+    Pair sets are partitioned by the pair's ROW: pairs[k] = [2, M_k] int64 with LOCAL row ids
+    (0..n_local) and GLOBAL column ids; labels[k][M_k].  The row operand P comes from this rank's
+    nodes, the column operand Q from the all-gathered layer input (projections recomputed locally:
+    F or D floats per node travel, not C*D).  n_pos_total[k] / m_total[k] are the positive count and
+    size of the WHOLE set k (all ranks), so the per-rank return values SUM to the reference's loss
+    and `allreduce_grads` yields its gradient.  ranges[k] = channel range consumed by set k."""
+    if layer_fn is None or pair_fn is None or loss_fn is None:
+        from . import functional as Fn
+        from .layers import run_channels
+        layer_fn = layer_fn or (lambda chs, x_need, graph: run_channels(chs, x_need, graph)[0])
+        pair_fn = pair_fn or Fn.PairScore.apply
+        loss_fn = loss_fn or Fn.SslWmse.apply
+    from .layers import pair_operands
+    x = F.dropout(x_local, enc.dropout, training=enc.training)
+    loss = None
+    for layer, chs in enumerate((enc.attentions1, enc.attentions2)):
+        if constrain_layer == 0 or constrain_layer == layer:
+            x_all = AllGatherRows.apply(x, part)
+            att, C, D, P, Q, a = pair_operands(chs, x, x_all)
+            for k, pr in enumerate(pairs):
+                lo, hi = ranges[k]
+                scores = pair_fn(att, C, D, pr[0], pr[1], lo, hi, P, Q, a)
+                term = loss_fn(scores, labels[k], n_pos_total[k], m_total[k])
+                loss = term if loss is None else loss + term
+        if layer == 0:       # layer-2 aggregation is dead compute for the pair losses (models.py:311-330)
+            out = layer_fn(chs, HaloExchange.apply(x, part), part.graph)
+            x = F.dropout(enc._fuse(0, fusers, out, x), enc.dropout, training=enc.training)
+    if loss is None:
+        raise ValueError("--constrain_layer=%d selects no layer" % constrain_layer)
+    return loss
+
+
+def sample_pairs_partitioned(part, pos_key_local, generator=None):
+    """This rank's share of `sample_train` (pretrainer.py:683-707) with the O(M) device sampler:
+    Bernoulli(3 rho) cells in the rows it owns (rho from the global edge count) united with a random
+    third of its own positives.  pos_key_local: sorted int64 keys i_global * n_total + j of its
+    positives.  Returns (pairs[2, M] with LOCAL rows / GLOBAL columns, label[M], n_pos_total, m_total)."""
+    from .sampler import sample_pairs_device
+    e_tot = torch.tensor([pos_key_local.numel()], dtype=torch.int64, device=pos_key_local.device)
+    if part.world > 1:
+        dist.all_reduce(e_tot)
+    idx, lab = sample_pairs_device(part.n_total, pos_key_local, generator, row_range=(part.lo, part.hi),
+                                   e_total=int(e_tot.item()))
+    cnt = torch.stack([(lab != 0).sum(), torch.tensor(lab.numel(), device=lab.device)]).to(torch.int64)
+    if part.world > 1:
+        dist.all_reduce(cnt)
+    pairs = torch.stack([idx[0] - part.lo, idx[1]])
+    return pairs, lab, int(cnt[0].item()), int(cnt[1].item())
+
+
 def allreduce_grads(params):
     """Sum the weight gradients over ranks (one flat bucket; the per-rank losses add up)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:

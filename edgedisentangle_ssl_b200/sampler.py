@@ -63,18 +63,23 @@ def sample_pairs(n, pos_indices, chunk_rows=None):
     return np.stack([key // n, key % n]), out_lab[:m].copy()
 
 
-def sample_pairs_device(n, pos_key, generator=None):
+def sample_pairs_device(n, pos_key, generator=None, row_range=None, e_total=None):
     """Distribution-equivalent sampler for graphs where N x N uniforms are not an option
     ('infeasible at N = 2.4 M').  Same law as `sample_pairs` -- an iid
     Bernoulli(3*rho) mask over the N x N cells, united with a uniformly random third of the
     positives -- but drawn in O(M): K ~ Binomial(N^2, 3*rho) (normal approximation), K distinct
     cells uniformly at random (draw, dedup, top up), union, sort, label.  Not bit-exact with the
     reference's RNG stream; runs entirely on the device of `pos_key` (sorted int64 keys i*n+j).
-    Returns (indices[2, M] int64, label[M] float32) on that device."""
+    Returns (indices[2, M] int64, label[M] float32) on that device.
+
+    row_range=(lo, hi), e_total: the slice of that sampler owned by one rank of a destination-range
+    partition -- cells restricted to rows [lo, hi) (pos_key = this rank's positives, global keys),
+    hit probability from the GLOBAL edge count; the union over ranks has the single-process law."""
     dev = pos_key.device
     e_l = pos_key.numel()
-    cells = float(n) * float(n)
-    thr = (torch.tensor(float(e_l), dtype=torch.float32) / (n * n)).item() * 3
+    lo, hi = (0, n) if row_range is None else row_range
+    cells = float(hi - lo) * float(n)
+    thr = (torch.tensor(float(e_l if e_total is None else e_total), dtype=torch.float32) / (n * n)).item() * 3
     mean, var = cells * thr, cells * thr * (1.0 - thr)
     z = torch.randn((), generator=generator, device=dev).item() if generator is not None else torch.randn(()).item()
     k = int(max(0, round(mean + (var ** 0.5) * z)))
@@ -82,9 +87,9 @@ def sample_pairs_device(n, pos_key, generator=None):
     need = k
     while need > 0:
         draw = int(need * 1.05) + 16
-        hi = torch.randint(0, n, (draw,), device=dev, generator=generator)
-        lo = torch.randint(0, n, (draw,), device=dev, generator=generator)
-        key = torch.unique(torch.cat([key, hi * n + lo]))
+        ri = torch.randint(lo, hi, (draw,), device=dev, generator=generator)
+        ci = torch.randint(0, n, (draw,), device=dev, generator=generator)
+        key = torch.unique(torch.cat([key, ri * n + ci]))
         if key.numel() > k:        # drop a random surplus so that exactly k distinct cells remain
             keep = torch.randperm(key.numel(), device=dev, generator=generator)[:k]
             key = key[keep]

@@ -221,12 +221,16 @@ int edis_pair_score_bwd(const edis_layer_desc* d, int64_t n, int64_t m, const in
  * utils.adj_mse_loss (utils.py:287-298, incl. its `shape[0]**2` total on 1-D targets).
  * scores[M, Cs] (the output of edis_pair_score_fwd for the consumed channel range).
  * fwd writes loss[0] (8-byte workspace for the double accumulator), bwd writes
- * g_scores[M, Cs] = g_loss[0] * dloss/dscores (g_loss is a device scalar). */
+ * g_scores[M, Cs] = g_loss[0] * dloss/dscores (g_loss is a device scalar).
+ * m_total: size of the WHOLE pair set when scores/target hold only this rank's slice of it
+ * (destination-partitioned multi-GPU run; n_pos is then the positive count of the whole set and
+ * the per-rank losses add up to the reference's loss); single GPU: m_total = m. */
 int edis_ssl_wmse_fwd(int64_t m, int32_t cs, const float* scores, const float* target,
-                      int64_t n_pos, float* loss, void* workspace, int64_t workspace_bytes,
-                      void* stream);
+                      int64_t n_pos, int64_t m_total, float* loss, void* workspace,
+                      int64_t workspace_bytes, void* stream);
 int edis_ssl_wmse_bwd(int64_t m, int32_t cs, const float* scores, const float* target,
-                      int64_t n_pos, const float* g_loss, float* g_scores, void* stream);
+                      int64_t n_pos, int64_t m_total, const float* g_loss, float* g_scores,
+                      void* stream);
 
 /* ------------------------------------------------------------------ DifHead tail
  * loss = mean_i -log_softmax(logits[i, :])[label] with ONE constant label for all rows

@@ -133,3 +133,118 @@ def test_row_ranges_and_compact_indexing():
     part = par.Partition(0, 1, b, idx[0], idx[1])
     assert part.n_src == n and len(part.halo_ids) == 0
     assert np.array_equal(part.col_local, idx[1]) and np.array_equal(part.row_local, idx[0])
+
+
+# ------------------------------------------------------------------ partitioned SSL pair loss
+def torch_pair_fn(att, C, D, pi, pj, c_lo, c_hi, P, Q, a):
+    """layers.py:349-389 on pair lists, plain torch (stands in for the CUDA PairScore on CPU)."""
+    if att == 1:
+        e = P[pi] + Q[pj]
+    elif att == 2:
+        e = (P[pi].reshape(-1, C, D) * Q[pj].reshape(-1, C, D)).sum(-1)
+    else:
+        e = (torch.nn.functional.leaky_relu(P[pi] + Q[pj], 0.01).reshape(-1, C, D) * a.reshape(1, C, D)).sum(-1)
+    return e[:, c_lo:c_hi]
+
+
+def torch_wmse(scores, target, n_pos, m_total):
+    """utils.adj_mse_loss (utils.py:287-298) on one slice of a pair set of m_total pairs."""
+    p = torch.sigmoid(scores.sum(1))
+    w_neg = n_pos / (float(m_total) ** 2 - n_pos)
+    w = torch.where(target != 0, torch.ones_like(p), torch.full_like(p, w_neg))
+    return (w * (p - target) ** 2).sum() / m_total
+
+
+def ssl_problem():
+    n, idx, args, enc, fus, x, R = make_problem()
+    rng = np.random.RandomState(11)
+    key = np.unique(np.concatenate([rng.randint(0, n * n, 900), idx[0][::3] * n + idx[1][::3]]))
+    pos = set((idx[0] * n + idx[1]).tolist())
+    lab = np.array([1.0 if k in pos else 0.0 for k in key], dtype=np.float32)
+    return n, idx, enc, fus, x, key, lab
+
+
+def ssl_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from edgedisentangle_ssl_b200 import parallel as par
+        n, idx, enc, fus, x, key, lab = ssl_problem()
+        rowptr = np.concatenate([[0], np.cumsum(np.bincount(idx[0], minlength=n))])
+        bounds = par.row_ranges(rowptr, world, balance="edges")
+        lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+        sel = (idx[0] >= lo) & (idx[0] < hi)
+        part = par.Partition(rank, world, bounds, idx[0][sel], idx[1][sel])
+        mine = (key // n >= lo) & (key // n < hi)
+        pairs = torch.from_numpy(np.stack([key[mine] // n - lo, key[mine] % n]))
+        labels = torch.from_numpy(lab[mine])
+
+        def layer_fn(chs, x_need, graph):
+            return oracle_layer(chs, x_need, part.row_local, part.col_local, part.n_local)
+
+        loss = par.ssl_pair_loss_partitioned(enc, fus, x[lo:hi], part, [pairs], [labels], [(0, 2)],
+                                             [int(lab.sum())], [len(key)], 0, layer_fn, torch_pair_fn, torch_wmse)
+        loss.backward()
+        par.allreduce_grads([p for m in [enc] + fus for p in m.parameters()])
+        out_q.put((rank, {"loss": float(loss.detach()), "m": int(mine.sum()),
+                          "grads": {k: v.grad.numpy().copy() for k, v in enc.named_parameters() if v.grad is not None}}))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_partitioned_ssl_pair_loss_matches_single_process():
+    """Pairs partitioned by row, Q from the all-gathered layer input, reduce-scatter in backward:
+    the rank losses add up to the single-process loss and the all-reduced gradients match."""
+    from edgedisentangle_ssl_b200 import parallel as par
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=ssl_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    n, idx, enc, fus, x, key, lab = ssl_problem()
+    part = par.Partition(0, 1, np.array([0, n]), idx[0], idx[1])
+
+    def layer_fn(chs, x_need, graph):
+        return oracle_layer(chs, x_need, part.row_local, part.col_local, part.n_local)
+
+    pairs = torch.from_numpy(np.stack([key // n, key % n]))
+    loss = par.ssl_pair_loss_partitioned(enc, fus, x, part, [pairs], [torch.from_numpy(lab)], [(0, 2)],
+                                         [int(lab.sum())], [len(key)], 0, layer_fn, torch_pair_fn, torch_wmse)
+    loss.backward()
+    assert sum(r["m"] for r in results.values()) == len(key) and min(r["m"] for r in results.values()) > 0
+    ref_loss = float(loss.detach())
+    assert abs(sum(r["loss"] for r in results.values()) - ref_loss) <= 1e-6 * abs(ref_loss) + 1e-9
+    seen = 0
+    for k, v in enc.named_parameters():
+        if v.grad is not None:
+            for r in range(world):
+                assert torch.allclose(torch.from_numpy(results[r]["grads"][k]), v.grad, rtol=2e-4, atol=1e-7), k
+            seen += 1
+    assert seen > 0
+
+
+def test_partition_sampler_rows_and_labels():
+    """sample_pairs_partitioned (world 1 here): rows local, columns global, labels = membership in
+    the positive set, a third of the positives forced in (pretrainer.py:696-700)."""
+    from edgedisentangle_ssl_b200 import parallel as par      # the sampler is device-agnostic torch code
+    rng = np.random.RandomState(5)
+    n = 300
+    idx, _ = og.build_adjacency(n, rng.randint(0, n, 2500), rng.randint(0, n, 2500))
+    part = par.Partition(0, 1, np.array([0, n]), idx[0], idx[1])
+    pos_key = torch.from_numpy(idx[0] * n + idx[1])
+    gen = torch.Generator().manual_seed(3)
+    pairs, lab, n_pos, m = par.sample_pairs_partitioned(part, pos_key, gen)
+    assert pairs.shape[0] == 2 and pairs.shape[1] == lab.numel() == m
+    key = pairs[0] * n + pairs[1]
+    assert torch.all(key[1:] > key[:-1])                                   # row-major sorted, deduplicated
+    member = torch.isin(key, pos_key)
+    assert torch.equal(member, lab != 0) and n_pos == int(member.sum())
+    assert n_pos >= pos_key.numel() // 3                                    # the forced third is inside
+    expect = 3.0 * pos_key.numel() + pos_key.numel() / 3.0                  # E[M] ~ 3E + E/3 (minus overlap)
+    assert 0.8 * expect < m < 1.1 * expect
