@@ -10,5 +10,5 @@ k = d['roofline']['kernels']
 print('$name', 'ms/step %.1f' % d['ms_per_step'], 'Medges/s %.1f' % (d['value']/1e6), ' '.join('%s=%.1f(%.0f/%.0f)' % (a.replace('disga_',''), b['ms_per_step'], b['gbs'], b['moved_gbs']) for a, b in k.items()))
 "
 }
-run stream X=1
-run nostream EDIS_LIB=$PWD/variants/libedis_nostream.so
+run kv4 X=1
+run kv2 EDIS_KV=2
