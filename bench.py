@@ -395,7 +395,7 @@ def main():
     # recorded per call by functional.kernel_bytes (layer 1 and layer 2 may run different plans)
     per = {}
     for k, v in kernel_list.items():
-        if not v:
+        if not v or kernel_bytes[k][0] is None:
             continue
         ms = np.array(v)
         alg_b = sum(m["alg"] for m in kernel_bytes[k])

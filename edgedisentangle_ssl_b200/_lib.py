@@ -74,9 +74,10 @@ SIGNATURES = {
                                     c_int64, _P]),
     "edis_disga_sage_fused_gx": (c_int, [_descp]),
     "edis_pair_score_fwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,
-                                    _P, c_int64, _P, _P, _P]),
+                                    _P, c_int64, _P, _P, _P, _P]),
     "edis_pair_score_bwd": (c_int, [_descp, c_int64, c_int64, _P, _P, c_int32, c_int32, _P, c_int64,
-                                    _P, c_int64, _P, _P, _P, _P, _P, _P]),
+                                    _P, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "edis_pair_sign_bytes": (c_int64, [_descp, c_int64, c_int32, c_int32]),
     "edis_ssl_wmse_fwd": (c_int, [c_int64, c_int32, _P, _P, c_int64, c_int64, _P, _P, c_int64, _P]),
     "edis_ssl_wmse_bwd": (c_int, [c_int64, c_int32, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "edis_nll_const_label_fwd": (c_int, [c_int64, c_int32, _P, c_int32, _P, _P, c_int64, _P]),

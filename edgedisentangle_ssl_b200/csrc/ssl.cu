@@ -20,6 +20,15 @@ struct PairArgs {
   float* out;
   const float* g_out;
   float *gP, *gQ, *ga;
+  // att 3 sign record (see edis_common.cuh): written by the forward, read by k_pair_bwd_sign
+  unsigned char* sign;
+  // k_pair_bwd_sign: one pass per side.  key = pi (row pass, perm == NULL) or pj (column pass,
+  // perm = pair ids sorted by j); X / ldx = the side's operand rows (P or Q), gX its gradient
+  const int64_t* key;
+  const int32_t *perm, *col_perm;
+  const float* X;
+  int64_t ldx;
+  float* gX;
 };
 
 template <class T, int ATT>
@@ -36,6 +45,7 @@ __global__ void __launch_bounds__(256) k_pair_fwd(const PairArgs A) {
     int cidx[NCH];
 #pragma unroll
     for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane);
+    constexpr int SBPL = (R + 7) / 8;
     float ar[R];
     if (ATT == 3) T::load(ar, A.a + off, lane, A.D);
     const int64_t base = blk * kPairBlock;
@@ -48,6 +58,7 @@ __global__ void __launch_bounds__(256) k_pair_fwd(const PairArgs A) {
       const int64_t i = __shfl_sync(FULL, myi, t);
       const int64_t j = __shfl_sync(FULL, myj, t);
       float e[NCH];
+      unsigned mask = 0u;
       if (ATT == 1) {
 #pragma unroll
         for (int k = 0; k < NCH; ++k) e[k] = __ldg(A.P + i * A.ldp + cidx[k]) + __ldg(A.Q + j * A.ldq + cidx[k]);
@@ -63,11 +74,21 @@ __global__ void __launch_bounds__(256) k_pair_fwd(const PairArgs A) {
         for (int k = 0; k < NCH; ++k) part[k] = 0.0f;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
-          if (ATT == 3) part[r / RPC] = fmaf(ar[r], lrelu01(pr[r] + q[r]), part[r / RPC]);
-          else part[r / RPC] = fmaf(pr[r], q[r], part[r / RPC]);
+          if (ATT == 3) {
+            const float w = -pr[r] - q[r];                 // -(P_i + Q_j): its sign bit <=> z > 0
+            mask = sign_push(mask, w);
+            part[r / RPC] = fmaf(ar[r], lrelu01(-w), part[r / RPC]);
+          } else {
+            part[r / RPC] = fmaf(pr[r], q[r], part[r / RPC]);
+          }
         }
 #pragma unroll
         for (int k = 0; k < NCH; ++k) e[k] = T::reduce(part[k]);
+        if (ATT == 3 && A.sign) {
+          const int64_t so = (((base + t) * A.G + grp) * 32 + lane) * SBPL;
+          if (SBPL == 1) st_stream(A.sign + so, static_cast<unsigned char>(mask));
+          else st_stream(reinterpret_cast<unsigned short*>(A.sign + so), static_cast<unsigned short>(mask));
+        }
       }
       if (T::writer(lane)) {
 #pragma unroll
@@ -155,8 +176,123 @@ __global__ void __launch_bounds__(256) k_pair_bwd(const PairArgs A) {
   if (ATT == 3 && da_grp >= 0) T::atomic_add(A.ga + (A.c_lo + da_grp * T::CPW) * A.D, da, lane, A.D);
 }
 
+// att 3 backward from the forward's sign record, one launch per side (no 2 KB atomic per pair, no
+// re-gather of the other side's rows): over runs of equal key (i: the list is row-sorted; j: through
+// the caller's column-sorted permutation) accumulate U = sum g * [z > 0] and S = sum g per channel;
+// at the run end  u = 0.99 U + 0.01 S,  da += X_key (.) u  (Euler, as in the layer kernels),
+// gX_key += a (.) u  (one vector reduction per run; runs may straddle 32-pair blocks).
+template <class T>
+__global__ void __launch_bounds__(256) k_pair_bwd_sign(const PairArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC;
+  constexpr int SBPL = (R + 7) / 8;
+  const int lane = threadIdx.x & 31;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * (blockDim.x >> 5);
+  int64_t unit = static_cast<int64_t>(blockIdx.x) * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int CD = A.C * A.D;
+  float da[R];
+  zero<T>(da);
+  int da_grp = -1;
+  for (; unit < A.n_units; unit += nwarps) {
+    const int64_t blk = unit / A.G;
+    const int grp = static_cast<int>(unit - blk * A.G);
+    const int c0 = A.c_lo + grp * T::CPW;
+    const int off = c0 * A.D;
+    if (grp != da_grp) {
+      if (da_grp >= 0) T::atomic_add(A.ga + (A.c_lo + da_grp * T::CPW) * A.D, da, lane, A.D);
+      zero<T>(da);
+      da_grp = grp;
+    }
+    int cidx[NCH];
+#pragma unroll
+    for (int k = 0; k < NCH; ++k) cidx[k] = c0 + T::ch(k, lane) - A.c_lo;
+    float ar[R];
+    T::load(ar, A.a + off, lane, A.D);
+    const int64_t base = blk * kPairBlock;
+    const int cnt = static_cast<int>(min(static_cast<int64_t>(kPairBlock), A.m - base));
+    int mypid = 0, mykey = 0;       // m < 2^31 (checked by the entry point), node ids < 2^31
+    if (lane < cnt) {
+      mypid = A.perm ? A.perm[base + lane] : static_cast<int>(base + lane);
+      mykey = static_cast<int>(A.key[mypid]);
+    }
+    int cur = -1;
+    float U[R], S[NCH];
+    auto flush = [&]() {
+      float x[R], o[R];
+      T::load(x, A.X + static_cast<int64_t>(cur) * A.ldx + off, lane, A.D);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float u = fmaf(0.99f, U[r], 0.01f * S[r / RPC]);
+        da[r] = fmaf(x[r], u, da[r]);
+        o[r] = ar[r] * u;
+      }
+      T::atomic_add(A.gX + static_cast<int64_t>(cur) * CD + off, o, lane, A.D);
+    };
+    // PU pairs in flight per warp: the record / gradient loads of a group are issued together
+    // (the column pass reads them at random addresses -- one pair at a time is latency-bound)
+    constexpr int PU = 4;
+    for (int t0 = 0; t0 < cnt; t0 += PU) {
+      int keys[PU];
+      unsigned sg[PU];
+      float g[PU][NCH];
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        const int t = min(t0 + u, cnt - 1);
+        const int64_t pid = __shfl_sync(FULL, mypid, t);
+        keys[u] = __shfl_sync(FULL, mykey, t);
+        const int64_t so = ((pid * A.G + grp) * 32 + lane) * SBPL;
+        sg[u] = SBPL == 1 ? static_cast<unsigned>(ld_stream(A.sign + so))
+                          : static_cast<unsigned>(ld_stream(reinterpret_cast<const unsigned short*>(A.sign + so)));
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) g[u][k] = __ldg(A.g_out + pid * A.Cs + cidx[k]);
+      }
+#pragma unroll
+      for (int u = 0; u < PU; ++u) {
+        if (t0 + u < cnt) {
+          if (keys[u] != cur) {
+            if (cur >= 0) flush();
+            cur = keys[u];
+            zero<T>(U);
+#pragma unroll
+            for (int k = 0; k < NCH; ++k) S[k] = 0.0f;
+          }
+#pragma unroll
+          for (int k = 0; k < NCH; ++k) {
+            S[k] += g[u][k];
+#pragma unroll
+            for (int r = k * RPC; r < (k + 1) * RPC; ++r) U[r] = fmaf(sign_pos_f<R>(sg[u], r), g[u][k], U[r]);
+          }
+        }
+      }
+    }
+    if (cur >= 0) flush();
+  }
+  if (da_grp >= 0) T::atomic_add(A.ga + (A.c_lo + da_grp * T::CPW) * A.D, da, lane, A.D);
+}
+
+template <class T>
+static int launch_pair_sign(PairArgs A, cudaStream_t st) {
+  A.G = A.Cs / T::CPW;
+  const int64_t blocks_of_pairs = (A.m + kPairBlock - 1) / kPairBlock;
+  A.n_units = blocks_of_pairs * A.G;
+  if (A.n_units == 0) return EDIS_OK;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  int blocks = launch_grid(reinterpret_cast<const void*>(&k_pair_bwd_sign<T>), 256, 0, sms);
+  const int64_t need = (A.n_units + 7) / 8;
+  if (need < blocks) blocks = static_cast<int>(need);
+  // row side (the list is sorted by i), then column side through the permutation
+  A.key = A.pi; A.perm = nullptr; A.X = A.P; A.ldx = A.ldp; A.gX = A.gP;
+  k_pair_bwd_sign<T><<<blocks, 256, 0, st>>>(A);
+  A.key = A.pj; A.perm = A.col_perm; A.X = A.Q; A.ldx = A.ldq; A.gX = A.gQ;
+  k_pair_bwd_sign<T><<<blocks, 256, 0, st>>>(A);
+  EDIS_CUDA(cudaGetLastError());
+  return EDIS_OK;
+}
+
 template <class T, int ATT>
 static int launch_pair(bool bwd, PairArgs A, cudaStream_t st) {
+  if (bwd && ATT == 3 && A.sign && A.col_perm) return launch_pair_sign<T>(A, st);
   A.G = A.Cs / T::CPW;
   const int64_t blocks_of_pairs = (A.m + kPairBlock - 1) / kPairBlock;
   A.n_units = blocks_of_pairs * A.G;
@@ -190,6 +326,11 @@ static int launch_pair_any(bool bwd, const PairArgs& A, int att, cudaStream_t st
   const int D = A.D, Cs = A.Cs;
   const bool aligned = att == 1 || ((reinterpret_cast<uintptr_t>(A.P) % 16 == 0) && (reinterpret_cast<uintptr_t>(A.Q) % 16 == 0) &&
                                     A.ldp % 4 == 0 && A.ldq % 4 == 0);
+  if (!aligned && A.sign) {
+    set_error("pair scoring with a sign record needs 16-byte aligned P / Q rows (ld %% 4 == 0)");
+    return EDIS_ERR_ARG;
+  }
+  // (whole-row warps, VecT<4,16>, measured slower here: pair fwd 94 vs 86 ms, bwd 158 vs 138 ms at M = 210M)
   if (aligned && D == 64 && Cs % 4 == 0) return launch_pair_att<VecT<2, 16>>(bwd, A, att, st);
   if (aligned && D == 64 && Cs % 2 == 0) return launch_pair_att<VecT<1, 16>>(bwd, A, att, st);
   if (aligned && D == 128) return launch_pair_att<VecT<1, 32>>(bwd, A, att, st);
@@ -370,28 +511,42 @@ static int pair_common(const char* who, const edis_layer_desc* d, int64_t n, int
   return EDIS_OK;
 }
 
+// bytes of the att-3 sign record of a pair list (layout private to the pair kernels)
+extern "C" int64_t edis_pair_sign_bytes(const edis_layer_desc* d, int64_t m, int32_t c_lo, int32_t c_hi) {
+  if (!d || m < 0 || c_hi <= c_lo) return EDIS_ERR_ARG;
+  if (d->att != 3) return 0;
+  const int cs = c_hi - c_lo;
+  // 32 lanes x SBPL bytes per (pair, channel group); channels per group as in launch_pair_any
+  const int cpw = d->D != 64 ? 1 : (cs % 4 == 0 ? 4 : (cs % 2 == 0 ? 2 : 1));
+  return m * static_cast<int64_t>(cs / cpw) * 32 + 64;
+}
+
 extern "C" int edis_pair_score_fwd(const edis_layer_desc* d, int64_t n, int64_t m, const int64_t* pi,
                                    const int64_t* pj, int32_t c_lo, int32_t c_hi, const float* P,
                                    int64_t ldp, const float* Q, int64_t ldq, const float* a,
-                                   float* out, void* stream) {
+                                   float* out, uint8_t* psign, void* stream) {
   PairArgs A = {};
   int rc = pair_common("edis_pair_score_fwd", d, n, m, pi, pj, c_lo, c_hi, P, Q, a, &A);
   if (rc) return rc;
   EDIS_CHECK_ARG(out || m == 0, "edis_pair_score_fwd: null out");
-  A.ldp = ldp; A.ldq = ldq; A.out = out;
+  A.ldp = ldp; A.ldq = ldq; A.out = out; A.sign = psign;
   return launch_pair_any(false, A, d->att, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int edis_pair_score_bwd(const edis_layer_desc* d, int64_t n, int64_t m, const int64_t* pi,
                                    const int64_t* pj, int32_t c_lo, int32_t c_hi, const float* P,
                                    int64_t ldp, const float* Q, int64_t ldq, const float* a,
-                                   const float* g_out, float* gP, float* gQ, float* ga, void* stream) {
+                                   const float* g_out, const uint8_t* psign, const int32_t* col_perm,
+                                   float* gP, float* gQ, float* ga, void* stream) {
   PairArgs A = {};
   int rc = pair_common("edis_pair_score_bwd", d, n, m, pi, pj, c_lo, c_hi, P, Q, a, &A);
   if (rc) return rc;
   EDIS_CHECK_ARG((g_out && gP && gQ) || m == 0, "edis_pair_score_bwd: null pointer");
   EDIS_CHECK_ARG(d->att != 3 || ga, "edis_pair_score_bwd: att=3 needs ga");
+  EDIS_CHECK_ARG((m < (int64_t(1) << 31) && n < (int64_t(1) << 31)) || !col_perm,
+                 "edis_pair_score_bwd: the sign-record path needs m, n < 2^31");
   A.ldp = ldp; A.ldq = ldq; A.g_out = g_out; A.gP = gP; A.gQ = gQ; A.ga = ga;
+  A.sign = const_cast<uint8_t*>(psign); A.col_perm = col_perm;
   return launch_pair_any(true, A, d->att, static_cast<cudaStream_t>(stream));
 }
 

@@ -421,12 +421,31 @@ class ChannelLinear(torch.autograd.Function):
         return g_agg, g_w
 
 
+class PairList:
+    """One (i, j) pair set [2, M] (int64, CUDA) plus what the kernels derive from it once per
+    set rather than once per layer: the column-sorted permutation the att-3 backward walks."""
+
+    def __init__(self, pairs):
+        self.pi, self.pj = pairs[0].contiguous(), pairs[1].contiguous()
+        self._perm = None
+
+    @staticmethod
+    def wrap(p):
+        return p if isinstance(p, PairList) else PairList(p)
+
+    def col_perm(self):
+        """Pair ids sorted by column j, int32 (one radix sort per sampled pair set)."""
+        if self._perm is None:
+            self._perm = torch.sort(self.pj.to(torch.int32))[1].to(torch.int32)
+        return self._perm
+
+
 class PairScore(torch.autograd.Function):
     """Raw attention logits of channels [c_lo, c_hi) on an arbitrary (i, j) pair list.
     Replaces layers.py:355-360 / 368-372 / 381-389.  Returns [M, c_hi - c_lo]."""
 
     @staticmethod
-    def forward(ctx, att, C, D, pi, pj, c_lo, c_hi, P, Q, a):
+    def forward(ctx, att, C, D, pi, pj, c_lo, c_hi, P, Q, a, plist=None):
         P, ldp = _rows(P, "P")
         Q, ldq = _rows(Q, "Q")
         a = a.contiguous() if a is not None else None
@@ -437,16 +456,24 @@ class PairScore(torch.autograd.Function):
         m, n = pi.numel(), P.shape[0]
         out = torch.empty(m, c_hi - c_lo, dtype=torch.float32, device=P.device)
         d = _desc(att, C, D)
-        check(lib.edis_pair_score_fwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
-                                      _ptr(Q), ldq, _ptr(a), _ptr(out), _stream()), "edis_pair_score_fwd")
+        psign = None
+        if att == 3 and any(ctx.needs_input_grad) and 0 < m < 2 ** 31 and ldp % 4 == 0 and ldq % 4 == 0 \
+                and P.data_ptr() % 16 == 0 and Q.data_ptr() % 16 == 0:
+            nb = check(lib.edis_pair_sign_bytes(ctypes.byref(d), m, c_lo, c_hi), "edis_pair_sign_bytes")
+            psign = torch.empty(int(nb), dtype=torch.uint8, device=P.device)
+        with _timed("pair_fwd", None, 1):
+            check(lib.edis_pair_score_fwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
+                                          _ptr(Q), ldq, _ptr(a), _ptr(out), _ptr(psign), _stream()),
+                  "edis_pair_score_fwd")
         ctx.d, ctx.rng, ctx.lds = d, (c_lo, c_hi), (ldp, ldq)
         ctx.has_a = a is not None
-        ctx.save_for_backward(pi, pj, P, Q, a)
+        ctx.plist = plist if plist is not None else (PairList(torch.stack([pi, pj])) if psign is not None else None)
+        ctx.save_for_backward(pi, pj, P, Q, a, psign)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        pi, pj, P, Q, a = ctx.saved_tensors
+        pi, pj, P, Q, a, psign = ctx.saved_tensors
         d = ctx.d
         c_lo, c_hi = ctx.rng
         ldp, ldq = ctx.lds
@@ -456,10 +483,12 @@ class PairScore(torch.autograd.Function):
         gQ = torch.zeros(Q.shape[0], wdt, dtype=torch.float32, device=P.device)   # P and Q may differ in rows
         ga = torch.zeros(d.C, d.D, dtype=torch.float32, device=P.device) if d.att == 3 else None
         g_out = g_out.contiguous()
-        check(lib.edis_pair_score_bwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
-                                      _ptr(Q), ldq, _ptr(a), _ptr(g_out), _ptr(gP), _ptr(gQ), _ptr(ga),
-                                      _stream()), "edis_pair_score_bwd")
-        return (None, None, None, None, None, None, None, gP, gQ, ga if ctx.has_a else None)
+        perm = ctx.plist.col_perm() if psign is not None else None
+        with _timed("pair_bwd", None, 2 if psign is not None else 1):
+            check(lib.edis_pair_score_bwd(ctypes.byref(d), n, m, _ptr(pi), _ptr(pj), c_lo, c_hi, _ptr(P), ldp,
+                                          _ptr(Q), ldq, _ptr(a), _ptr(g_out), _ptr(psign), _ptr(perm), _ptr(gP),
+                                          _ptr(gQ), _ptr(ga), _stream()), "edis_pair_score_bwd")
+        return (None, None, None, None, None, None, None, gP, gQ, ga if ctx.has_a else None, None)
 
 
 class SslWmse(torch.autograd.Function):

@@ -18,7 +18,7 @@ from torch import nn
 from torch.nn.parameter import Parameter
 
 from . import _lib
-from .functional import ChannelLinear, DisGAFused, PairScore, Proj3xTF32, SageFused
+from .functional import ChannelLinear, DisGAFused, PairList, PairScore, Proj3xTF32, SageFused
 from .graph import as_graph
 
 _seed_counter = itertools.count(1)
@@ -125,7 +125,8 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
         auxs = []
         for k, pairs in enumerate(aux):
             lo, hi = (0, C) if aux_ranges is None else aux_ranges[k]
-            auxs.append(PairScore.apply(att, C, D, pairs[0], pairs[1], lo, hi, P, Q, a))
+            pl = PairList.wrap(pairs)
+            auxs.append(PairScore.apply(att, C, D, pl.pi, pl.pj, lo, hi, P, Q, a, pl))
     if not aggregate:
         return None, None, auxs
     training, p = l0.training, l0.dropout

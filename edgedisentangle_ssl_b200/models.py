@@ -76,6 +76,9 @@ class DISGAT(nn.Module):
         if not isinstance(fusers, list):
             fusers = [fusers]
         graph = as_graph(adj)
+        if aux is not None:
+            from .functional import PairList
+            aux = [PairList.wrap(p) for p in aux]     # per-set derived data shared by both layers
         res = dict(x_in=[], out=[], edge_e=[], aux=[], fused=[])
         x = F.dropout(x, self.dropout, training=self.training)
         for layer, chs in enumerate((self.attentions1, self.attentions2)):

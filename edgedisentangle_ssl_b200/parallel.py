@@ -198,7 +198,9 @@ def ssl_pair_loss_partitioned(enc, fusers, x_local, part, pairs, labels, ranges,
         layer_fn = layer_fn or (lambda chs, x_need, graph: run_channels(chs, x_need, graph)[0])
         pair_fn = pair_fn or Fn.PairScore.apply
         loss_fn = loss_fn or Fn.SslWmse.apply
+    from .functional import PairList
     from .layers import pair_operands
+    pairs = [PairList.wrap(p) for p in pairs]
     x = F.dropout(x_local, enc.dropout, training=enc.training)
     loss = None
     for layer, chs in enumerate((enc.attentions1, enc.attentions2)):
@@ -207,7 +209,7 @@ def ssl_pair_loss_partitioned(enc, fusers, x_local, part, pairs, labels, ranges,
             att, C, D, P, Q, a = pair_operands(chs, x, x_all)
             for k, pr in enumerate(pairs):
                 lo, hi = ranges[k]
-                scores = pair_fn(att, C, D, pr[0], pr[1], lo, hi, P, Q, a)
+                scores = pair_fn(att, C, D, pr.pi, pr.pj, lo, hi, P, Q, a, pr)
                 term = loss_fn(scores, labels[k], n_pos_total[k], m_total[k])
                 loss = term if loss is None else loss + term
         if layer == 0:       # layer-2 aggregation is dead compute for the pair losses (models.py:311-330)

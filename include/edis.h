@@ -206,14 +206,22 @@ int edis_disga_sage_fused_gx(const edis_layer_desc* d);
  * Replaces layers.py:355-360 / 368-372 / 381-389 (`edge_auxs`).  pi/pj: int64 device arrays.
  * out[M, c_hi-c_lo].  Backward accumulates into gP/gQ/ga with vector atomics (caller
  * zero-fills or passes buffers that already hold other contributions). */
+/*   psign     att 3, optional: edis_pair_sign_bytes(...) bytes; the forward records one sign bit per
+ *             element of P_i + Q_j for every pair (as the layer kernels do per edge)
+ *   col_perm  att 3, optional (with psign): int32[M], the pair ids sorted by j.  With both, the
+ *             backward runs as two run-length passes over the sign record (rows in list order,
+ *             columns through col_perm): ~100 B per pair instead of re-gathering Q_j and a 2 KB
+ *             atomic per pair.  Without them (or att 1 / 2) it re-gathers and uses vector atomics. */
 int edis_pair_score_fwd(const edis_layer_desc* d, int64_t n, int64_t m, const int64_t* pi,
                         const int64_t* pj, int32_t c_lo, int32_t c_hi,
                         const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
-                        float* out, void* stream);
+                        float* out, uint8_t* psign, void* stream);
 int edis_pair_score_bwd(const edis_layer_desc* d, int64_t n, int64_t m, const int64_t* pi,
                         const int64_t* pj, int32_t c_lo, int32_t c_hi,
                         const float* P, int64_t ldp, const float* Q, int64_t ldq, const float* a,
-                        const float* g_out, float* gP, float* gQ, float* ga, void* stream);
+                        const float* g_out, const uint8_t* psign, const int32_t* col_perm,
+                        float* gP, float* gQ, float* ga, void* stream);
+int64_t edis_pair_sign_bytes(const edis_layer_desc* d, int64_t m, int32_t c_lo, int32_t c_hi);
 
 /* ------------------------------------------------------------------ fused SSL edge loss
  * loss = mean_k w_k (sigmoid(sum_c s[k,c]) - t_k)^2,  w = 1 on t != 0, else P/(M*M - P),

@@ -136,7 +136,7 @@ def test_row_ranges_and_compact_indexing():
 
 
 # ------------------------------------------------------------------ partitioned SSL pair loss
-def torch_pair_fn(att, C, D, pi, pj, c_lo, c_hi, P, Q, a):
+def torch_pair_fn(att, C, D, pi, pj, c_lo, c_hi, P, Q, a, plist=None):
     """layers.py:349-389 on pair lists, plain torch (stands in for the CUDA PairScore on CPU)."""
     if att == 1:
         e = P[pi] + Q[pj]
