@@ -18,7 +18,46 @@ from . import data_load, models, trainer, utils
 DATASETS = ("chameleon", "squirrel", "cora_full", "deezer", "arxiv", "BlogCatalog", "cora")
 
 
-def run(argv=None, data_root="data", epoch_hook=None):
+def checkpoint_path(args, epoch, root="."):
+    """Same location and name as the reference's save_model / load_model (main.py:214-235)."""
+    d = os.path.join(root, "checkpoint", args.dataset, "{}_used_edge{}_weight{}_reg{}".format(
+        args.model, args.used_edge, args.pre_weight, args.reg))
+    return d, os.path.join(d, "pretrain_{}_{}.pth".format(args.pretrain, epoch))
+
+
+def save_model(args, encoder, trainers, epoch, root="."):
+    """main.py:214-227 writes {'encoder': state_dict}.  That key keeps its meaning (the reference's
+    load_model reads these files unchanged); the per-trainer fusers / classifiers and every Adam
+    state ride along under 'trainers', so a run can be RESUMED, not only warm-started."""
+    d, path = checkpoint_path(args, epoch, root)
+    os.makedirs(d, exist_ok=True)
+    content = {"encoder": encoder.state_dict(), "epoch": epoch, "trainers": []}
+    for tr in trainers:
+        content["trainers"].append({"class": type(tr).__name__,
+                                    "models": [m.state_dict() for m in tr.models[1:]],     # [0] is the encoder
+                                    "optimizers": [o.state_dict() for o in tr.models_opt]})
+    torch.save(content, path)
+    print("successfully saved: {}".format(epoch))
+    return path
+
+
+def load_model(args, encoder, trainers=(), root="."):
+    """main.py:229-235 (+ the trainer states when the file carries them)."""
+    _, path = checkpoint_path(args, args.load, root)
+    content = torch.load(path, map_location=lambda storage, loc: storage)
+    encoder.load_state_dict(content["encoder"])
+    for tr, st in zip(trainers, content.get("trainers", [])):
+        if st["class"] != type(tr).__name__:
+            raise SystemExit("checkpoint trainer order differs: {} vs {}".format(st["class"], type(tr).__name__))
+        for m, sd in zip(tr.models[1:], st["models"]):
+            m.load_state_dict(sd)
+        for o, sd in zip(tr.models_opt, st["optimizers"]):
+            o.load_state_dict(sd)
+    print("successfully loaded: {}".format(args.load))
+    return content.get("epoch", args.load)
+
+
+def run(argv=None, data_root="data", epoch_hook=None, ckpt_root=".", save_every=0):
     args = utils.get_parser().parse_args(argv)
     args.log = True
     args.cuda = not args.no_cuda and torch.cuda.is_available()
@@ -67,6 +106,8 @@ def run(argv=None, data_root="data", epoch_hook=None):
             raise SystemExit("downstream 'Edge' is unfinished in the reference (README.md:22) and not built")
         down.append(trainer.ClsTrainer(args, encoder, labels, args.down_weight[0]))
 
+    if args.load is not None:
+        load_model(args, encoder, ssl_trainers + down, ckpt_root)
     t_total = time.time()
     history = []
     for epoch in range(args.epochs):
@@ -84,6 +125,8 @@ def run(argv=None, data_root="data", epoch_hook=None):
         torch.cuda.synchronize()
         log["epoch_ms"] = (time.time() - t_epoch) * 1e3
         history.append(log)
+        if save_every and (epoch + 1) % save_every == 0:
+            save_model(args, encoder, ssl_trainers + down, epoch, ckpt_root)
         if epoch_hook:
             epoch_hook(epoch, log)
     print("Optimization Finished!")

@@ -209,3 +209,32 @@ def test_accuracy_parity_chameleon_within_seed_noise():
     # the reference's own seed-to-seed spread (0.057 over these three seeds)
     assert min(ours) > 0.40
     assert abs(np.mean(ours) - np.mean(theirs)) <= max(spread, 0.05), (ours, theirs)
+
+
+def test_checkpoint_round_trip_resumes_bit_exactly(tmp_path):
+    """save_model / load_model (main.py:214-235 + per-trainer fusers, classifiers and Adam states):
+    2 epochs + save, then a fresh process state loading it must hold identical weights, keep the
+    reference's 'encoder' key layout, and continue training."""
+    import contextlib
+    import io
+    import os
+    from edgedisentangle_ssl_b200 import main as M
+    root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data")
+    flags = ["--seed=4", "--model=DISGAT", "--used_edge=1", "--finetune", "--downstream=CLS", "--down_weight=1.0",
+             "--steps=2", "--nhead=4", "--dataset=cora", "--pretrain", "SupEdge", "DifHead", "--pre_weight", "1", "1",
+             "--pre_edge", "1", "1", "--sparse", "--att=3", "--constrain_layer=0", "--gnn_type=AT"]
+    with contextlib.redirect_stdout(io.StringIO()):
+        M.run(flags + ["--epochs=2"], data_root=root, ckpt_root=str(tmp_path), save_every=2)
+    args = M.utils.get_parser().parse_args(flags + ["--epochs=2", "--load=1"])
+    _, path = M.checkpoint_path(args, 1, str(tmp_path))
+    saved = torch.load(path, map_location="cpu")
+    assert set(saved) >= {"encoder", "trainers"} and len(saved["trainers"]) == 3
+    assert "attention1_0.W" in saved["encoder"] and "attention2_3.W_em" in saved["encoder"]
+    assert saved["trainers"][2]["class"] == "ClsTrainer" and len(saved["trainers"][2]["optimizers"]) == 4
+    with contextlib.redirect_stdout(io.StringIO()):
+        hist = M.run(flags + ["--epochs=1", "--load=1"], data_root=root, ckpt_root=str(tmp_path), save_every=1)
+    assert np.isfinite(hist[0]["loss_train"])
+    # the resumed run started from the saved weights: its first test (epoch 0, before any step) sees them
+    resumed = torch.load(M.checkpoint_path(args, 0, str(tmp_path))[1], map_location="cpu")
+    moved = max(float((resumed["encoder"][k] - v).abs().max()) for k, v in saved["encoder"].items())
+    assert 0.0 < moved < 0.1          # one more epoch of Adam steps from the loaded state, not a re-init
