@@ -392,6 +392,53 @@ class Proj3xTF32(torch.autograd.Function):
         return gx, gw
 
 
+def _mm_3xtf32(x, w):
+    """x @ w at fp32 accuracy on the tensor cores (see Proj3xTF32): for SMALL inner dimensions only --
+    the operands are concatenated along K, and TF32 accumulation over very long K loses ~1e-3."""
+    xh, wh = _tf32_hi(x), _tf32_hi(w)
+    xc = torch.cat([xh, xh, x - xh], 1)
+    wc = torch.cat([wh, w - wh, wh], 0)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        return xc @ wc
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+class NodeLinear(torch.autograd.Function):
+    """F.linear(x, weight, bias) for a node tensor x[N, in] with N in the millions (FuseLayer,
+    layers.py:896-921).  Forward = the library fp32 GEMM.  Backward: the input gradient
+    g[N, out] @ weight[out, in] has a tiny inner dimension (out = nhid) and is bound by writing
+    [N, in] -> 3xTF32 on the tensor cores; the weight gradient reduces over N -> slab-wise fp32."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return torch.nn.functional.linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            gx = _mm_3xtf32(g, weight) if weight.shape[0] <= 128 else g @ weight
+        if ctx.needs_input_grad[1]:
+            gw = _xt_g(g, x)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = g.sum(0)
+        return gx, gw, gb
+
+
+def node_linear(lin, x):
+    """nn.Linear `lin` applied to a node tensor; the custom backward only where it pays."""
+    if x.is_cuda and x.dim() == 2 and x.shape[0] >= 262144 and x.dtype == torch.float32:
+        return NodeLinear.apply(x, lin.weight, lin.bias)
+    return lin(x)
+
+
 class ChannelLinear(torch.autograd.Function):
     """out[:, c*D:(c+1)*D] = agg[:, c*F:(c+1)*F] @ W[c]  for every channel c (plain cuBLAS GEMMs
     writing straight into column blocks: no [C, N, .] transposes).  agg [N, C*F], W [C, F, D]."""

@@ -18,7 +18,7 @@ from torch import nn
 from torch.nn.parameter import Parameter
 
 from . import _lib
-from .functional import ChannelLinear, DisGAFused, PairList, PairScore, Proj3xTF32, SageFused
+from .functional import ChannelLinear, DisGAFused, PairList, PairScore, Proj3xTF32, SageFused, node_linear
 from .graph import as_graph
 
 _seed_counter = itertools.count(1)
@@ -250,13 +250,13 @@ class FuseLayer(nn.Module):
         if rt == 0:
             if use_res:
                 features = torch.cat([features, residue], dim=-1)
-            feature = self.fuse(features)
+            feature = node_linear(self.fuse, features)
         elif rt == 1:
             if use_res:
                 features = torch.cat([features, residue], dim=-1)
-            feature = self.fuse2(F.leaky_relu(self.fuse(features)))
+            feature = node_linear(self.fuse2, F.leaky_relu(node_linear(self.fuse, features)))
         elif rt == 2:
-            feature = self.fuse(features)
+            feature = node_linear(self.fuse, features)
             if use_res:
-                feature = feature + self.fuse2(residue)
+                feature = feature + node_linear(self.fuse2, residue)
         return feature if self.args.fuse_no_relu else F.leaky_relu(feature)

@@ -512,3 +512,22 @@ def test_large_graph_properties(n, raw, at_plan):
     lhs = ((o - big) * R).sum().double().item()
     rhs = (gV * V1).sum().double().item()
     assert abs(lhs - rhs) <= 1e-4 * max(abs(lhs), 1.0), (lhs, rhs)
+
+
+def test_node_linear_backward_matches_float64():
+    """FuseLayer's Linear on a node tensor large enough for the custom backward (3xTF32 input
+    gradient, slab-wise weight gradient): same numbers as the float64 evaluation to fp32 accuracy."""
+    from edgedisentangle_ssl_b200.functional import node_linear
+    torch.manual_seed(0)
+    n, fin, fout = 300_000, 512, 64
+    lin = torch.nn.Linear(fin, fout).to(DEV)
+    x = torch.randn(n, fin, device=DEV, requires_grad=True)
+    r = torch.randn(n, fout, device=DEV)
+    (node_linear(lin, x) * r).sum().backward()
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = lin.weight.detach().double().requires_grad_(True)
+    b64 = lin.bias.detach().double().requires_grad_(True)
+    ((x64 @ w64.t() + b64) * r.double()).sum().backward()
+    assert_close(x.grad.cpu(), x64.grad.float().cpu(), 2e-6, "gx")
+    assert_close(lin.weight.grad.cpu(), w64.grad.float().cpu(), 2e-5, "gw")
+    assert_close(lin.bias.grad.cpu(), b64.grad.float().cpu(), 2e-5, "gb")
