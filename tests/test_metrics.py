@@ -27,3 +27,35 @@ def test_macro_f1_ignores_classes_absent_from_truth_and_prediction():
     _, f1 = roc_f_device(out, y)
     from sklearn.metrics import f1_score
     assert abs(float(f1) - f1_score(y, out.argmax(-1), average="macro")) < 1e-12
+
+
+@pytest.mark.parametrize("rt", [0, 1, 2])
+@pytest.mark.parametrize("use_res", [0, 1])
+@pytest.mark.parametrize("no_relu", [0, 1])
+def test_fuse_layer_variants_match_reference_golden(rt, use_res, no_relu):
+    """layers.FuseLayer (layers.py:876-921): every --residue_type x residue x --fuse_no_relu variant,
+    same state_dict keys, outputs and gradients as the unmodified reference
+    (tests/golden/make_golden_fuse.py).  Pure torch at this size: runs on CPU."""
+    import os
+    import numpy as np
+    import edgedisentangle_ssl_b200 as edis
+    from edgedisentangle_ssl_b200.utils import get_parser
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "fuse_variants.npz"))
+    tag = "rt%d_res%d_norelu%d" % (rt, use_res, no_relu)
+    args = get_parser().parse_args(["--residue_type=%d" % rt] + (["--fuse_no_relu"] if no_relu else []))
+    x = [torch.from_numpy(a).clone().requires_grad_(True) for a in g["x"]]
+    r = torch.from_numpy(g["r"])
+    f = edis.FuseLayer(args, len(x), nfeat=x[0].shape[1], residue=r.shape[1] if use_res else 0)
+    ref_sd = {k[len(tag) + 4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith(tag + ".sd.")}
+    assert set(ref_sd) == set(f.state_dict())
+    f.load_state_dict(ref_sd)
+    y = f(x, r if use_res else None)
+    y.pow(2).sum().backward()
+    assert torch.allclose(y.detach(), torch.from_numpy(g[tag + ".y"]), rtol=1e-6, atol=1e-7)
+    assert torch.allclose(x[0].grad, torch.from_numpy(g[tag + ".gx0"]), rtol=1e-5, atol=1e-7)
+    for k, v in f.named_parameters():
+        ref = torch.from_numpy(g[tag + ".g." + k])
+        assert torch.allclose(v.grad, ref, rtol=1e-5, atol=1e-6), k
+    # the channel-fused [N, C*D] tensor is accepted directly (the cat is free on the B200 path)
+    y2 = f(torch.cat([t.detach() for t in x], 1), r if use_res else None)
+    assert torch.allclose(y2, y.detach(), rtol=0, atol=0)
