@@ -1065,8 +1065,13 @@ static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc
   A.esign = const_cast<uint8_t*>(esign);
   A.ldgp = ldgp; A.ldgq = ldgq; A.ldgv = ldgv;
   A.pwidth = pw;
+  // heat level from which a gathered row is held in L2 (evict_last): the forward gathers 4 KB per
+  // source (Q_j | V_j), the backward passes 2 KB (V_j resp. gh_i), so they can afford a larger hot set
+  static const int hot_dst = env_int("EDIS_HOT_MIN_DST", 2);
+  static const int hot_src = env_int("EDIS_HOT_MIN_SRC", 2);
   if (phases & 1) {
     A.nbr = g->col;
+    A.hot_min = hot_dst;
     rc = launch_layer(Pass::BwdDst, g, A, d->att, st);
     if (rc) return rc;
     if (g->dst.n_split > 0) {
@@ -1076,7 +1081,10 @@ static int disga_bwd_impl(int phases, const edis_graph* g, const edis_layer_desc
       EDIS_CUDA(cudaGetLastError());
     }
   }
-  if (phases & 2) return bwd_score_src(g, d, A, false, gQ, gV, st);
+  if (phases & 2) {
+    A.hot_min = hot_src;
+    return bwd_score_src(g, d, A, false, gQ, gV, st);
+  }
   return EDIS_OK;
 }
 

@@ -10,5 +10,8 @@ k = d['roofline']['kernels']
 print('$name', 'ms/step %.1f' % d['ms_per_step'], 'Medges/s %.1f' % (d['value']/1e6), ' '.join('%s=%.1f(%.0f/%.0f)' % (a.replace('disga_',''), b['ms_per_step'], b['gbs'], b['moved_gbs']) for a, b in k.items()))
 "
 }
-run kv4 X=1
-run kv2 EDIS_KV=2
+run base X=1
+run src1 EDIS_HOT_MIN_SRC=1
+run src0 EDIS_HOT_MIN_SRC=0
+run dst1 EDIS_HOT_MIN_DST=1
+run src3 EDIS_HOT_MIN_SRC=3
