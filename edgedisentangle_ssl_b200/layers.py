@@ -148,9 +148,44 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
         h = ChannelLinear.apply(agg, w_em)
         out = F.elu(h + bias if bias is not None else h)
     else:
-        out, edge_e = DisGAFused.apply(graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias,
-                                       training, p, seed)
+        with _maybe_recompute(proj, x, w_all, lean=(aux is None and att != 1)):
+            out, edge_e = DisGAFused.apply(graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias,
+                                           training, p, seed)
     return out, edge_e, auxs
+
+
+class _Recompute:
+    """Marker packed in place of the saved projection (see _maybe_recompute)."""
+
+
+def _maybe_recompute(proj, x, w_all, lean):
+    """Memory-lean mode: `proj[N, 3*C*D]` is 6 KB per source row and layer and is the largest tensor
+    the fused layer saves for its backward.  With EDIS_RECOMPUTE_PROJ=1 -- or automatically when one
+    projection exceeds an eighth of the device memory -- the autograd graph keeps a marker instead
+    and the backward recomputes it from (x, W) with the same GEMM (bit-identical; ~3 ms per layer
+    at config A), so it is resident for one layer at a time instead of for every layer."""
+    import contextlib
+    mode = os.environ.get("EDIS_RECOMPUTE_PROJ", "auto")
+    if not lean or mode == "0" or not proj.is_cuda or not proj.requires_grad:
+        return contextlib.nullcontext()
+    if mode != "1":
+        total = torch.cuda.get_device_properties(proj.device).total_memory
+        if proj.numel() * 4 * 8 < total:
+            return contextlib.nullcontext()
+    key, shape = proj.data_ptr(), proj.shape
+    xd, wd = x.detach(), w_all.detach()
+    use3x = os.environ.get("EDIS_PROJ3X", "1") != "0" and x.shape[0] >= 4096
+
+    def pack(t):
+        return _Recompute if (t.data_ptr() == key and t.shape == shape) else t
+
+    def unpack(h):
+        if h is _Recompute:
+            from .functional import _mm_3xtf32
+            return _mm_3xtf32(xd, wd) if use3x else xd @ wd
+        return h
+
+    return torch.autograd.graph.saved_tensors_hooks(pack, unpack)
 
 
 def pair_operands(chs, x_dst, x_src):
