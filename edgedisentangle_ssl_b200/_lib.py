@@ -87,6 +87,7 @@ SIGNATURES = {
     "edis_sp_matmul_fwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P]),
     "edis_sp_matmul_bwd": (c_int, [c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, _P, _P, _P]),
     "edis_merge_pairs_host": (c_int64, [c_int64, _i64p, c_int64, _i64p, c_int64, _i64p, _i64p, _f32p]),
+    "edis_rand_hits_host": (c_int64, [c_void_p, c_int64, c_int64, ctypes.c_uint32, _i64p, c_int64]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

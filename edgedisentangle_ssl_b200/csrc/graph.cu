@@ -366,3 +366,84 @@ extern "C" int64_t edis_merge_pairs_host(int64_t n_hit, const int64_t* hit_key, 
   }
   return m;
 }
+
+// ---------------------------------------------------------------------------------------
+// Bit-exact replay of `(torch.rand(n_draws) < thr).nonzero()` on torch's CPU generator without
+// materialising the uniforms (pretrainer.py:692 draws N x N of them per sample_train call).
+//   state   the 5056-byte blob of torch.get_rng_state(): CPUGeneratorImplState =
+//           { u64 seed; i32 left; i32 seeded; u64 next; u64 mt[624]; normal-cache fields ... }
+//           (aten/src/ATen/CPUGeneratorImpl.cpp); advanced IN PLACE by n_draws 32-bit outputs, so
+//           torch.set_rng_state(state) afterwards leaves the generator exactly where the
+//           reference's torch.rand would have left it.
+//   thr24   the float32 threshold as an integer: a float32 uniform is (y & 0xFFFFFF) * 2^-24
+//           (ATen/core/TransformationHelper.h uniform_real<float>), so  u < thr  <=>
+//           (y & 0xFFFFFF) < ceil(float32(thr) * 2^24)
+//   out     linear draw indices of the hits (row-major: k = i * N + j), ascending; capacity `cap`
+// Returns the number of hits, or -(hits needed) if cap is too small (state untouched then).
+// The engine is ATen's mt19937 (ATen/core/MT19937RNGEngine.h): standard MT19937, `left` counts
+// the outputs remaining in the current 624-word block, regenerated when --left == 0.
+extern "C" int64_t edis_rand_hits_host(uint8_t* state, int64_t state_bytes, int64_t n_draws,
+                                       uint32_t thr24, int64_t* out, int64_t cap) {
+  if (!state || state_bytes < 24 + 624 * 8 || n_draws < 0 || (!out && cap > 0)) {
+    set_error("edis_rand_hits_host: bad arguments (state must be torch's 5056-byte CPU generator state)");
+    return EDIS_ERR_ARG;
+  }
+  constexpr int N = 624, M = 397;
+  int32_t left;
+  uint64_t next64;
+  uint32_t mt[N];
+  std::memcpy(&left, state + 8, 4);
+  std::memcpy(&next64, state + 16, 8);
+  for (int i = 0; i < N; ++i) {
+    uint64_t v;
+    std::memcpy(&v, state + 24 + 8 * i, 8);
+    mt[i] = static_cast<uint32_t>(v);
+  }
+  uint32_t next = static_cast<uint32_t>(next64);
+  auto twist = [](uint32_t u, uint32_t v) {
+    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
+  };
+  auto regenerate = [&]() {
+    uint32_t* p = mt;
+    for (int j = N - M + 1; --j; ++p) *p = p[M] ^ twist(p[0], p[1]);
+    for (int j = M; --j; ++p) *p = p[M - N] ^ twist(p[0], p[1]);
+    *p = p[M - N] ^ twist(p[0], mt[0]);
+    left = N;
+    next = 0;
+  };
+  int64_t hits = 0, k = 0;
+  while (k < n_draws) {
+    if (--left == 0) regenerate();
+    // outputs available without another regeneration: this one plus (left - 1) more
+    const int64_t run = std::min<int64_t>(n_draws - k, static_cast<int64_t>(left));
+    // two phases so that the tempering vectorises: temper a block, then scan it for the (rare) hits
+    uint32_t tmp[N];
+    const uint32_t* src = mt + next;
+    for (int t = 0; t < static_cast<int>(run); ++t) {
+      uint32_t y = src[t];
+      y ^= (y >> 11);
+      y ^= (y << 7) & 0x9d2c5680u;
+      y ^= (y << 15) & 0xefc60000u;
+      y ^= (y >> 18);
+      tmp[t] = y & 0xFFFFFFu;
+    }
+    for (int t = 0; t < static_cast<int>(run); ++t) {
+      if (tmp[t] < thr24) {
+        if (hits < cap) out[hits] = k + t;
+        ++hits;
+      }
+    }
+    next += static_cast<uint32_t>(run);
+    left -= static_cast<int32_t>(run - 1);
+    k += run;
+  }
+  if (hits > cap) return -hits;
+  std::memcpy(state + 8, &left, 4);
+  next64 = next;
+  std::memcpy(state + 16, &next64, 8);
+  for (int i = 0; i < N; ++i) {
+    const uint64_t v = mt[i];
+    std::memcpy(state + 24 + 8 * i, &v, 8);
+  }
+  return hits;
+}

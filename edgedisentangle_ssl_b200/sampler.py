@@ -24,6 +24,31 @@ def homo_hetero_split(indices, labels):
     return np.ascontiguousarray(indices[:, same]), np.ascontiguousarray(indices[:, ~same])
 
 
+def bernoulli_hits(n_draws, thr):
+    """Sorted linear indices k with u_k < thr, where u = torch.rand(n_draws) on torch's CPU default
+    generator -- same hits and same generator state afterwards as drawing the uniforms (bit-exact),
+    but the MT19937 stream is replayed in libedis.so and only the hits are stored
+    (`edis_rand_hits_host`): ~4x faster than torch.rand + compare + nonzero and O(hits) memory."""
+    st = torch.get_rng_state()
+    if st.numel() != 5056:                       # unknown generator layout: do it the slow way
+        return None
+    thr32 = float(np.float32(thr))               # `tensor(float32) < python float` compares in float32
+    thr24 = int(min(max(np.ceil(thr32 * 16777216.0), 0), 16777216))
+    buf = st.numpy().copy()
+    cap = int(n_draws * thr32 * 1.05) + 4096
+    while True:
+        out = np.empty(cap, dtype=np.int64)
+        work = buf.copy()
+        m = lib.edis_rand_hits_host(work.ctypes.data, work.nbytes, int(n_draws), thr24, np_ptr(out, c_int64), cap)
+        if m >= 0:
+            break
+        if m > -16:                              # EDIS_ERR_* codes, not a (negative) hit count
+            check(m, "edis_rand_hits_host")
+        cap = -int(m) + 16
+    torch.set_rng_state(torch.from_numpy(work))
+    return out[:m]
+
+
 def sample_pairs(n, pos_indices, chunk_rows=None):
     """One `sample_train` draw for one label set.
 
@@ -35,16 +60,18 @@ def sample_pairs(n, pos_indices, chunk_rows=None):
     e_l = pos_indices.shape[1]
     # pretrainer.py:690-692: float32 tensor division, then python-double * 3
     thr = (torch.tensor(float(e_l), dtype=torch.float32) / (n * n)).item() * 3
-    if chunk_rows is None:
-        chunk_rows = max(1, min(n, (1 << 24) // max(n, 1)))
-    hits = []
-    for r0 in range(0, n, chunk_rows):
-        r1 = min(n, r0 + chunk_rows)
-        nz = (torch.rand(size=(r1 - r0, n)) < thr).nonzero()
-        if nz.numel():
-            nz = nz.numpy()
-            hits.append((nz[:, 0].astype(np.int64) + r0) * n + nz[:, 1])
-    hit = np.concatenate(hits) if hits else np.empty(0, dtype=np.int64)
+    hit = bernoulli_hits(n * n, thr) if chunk_rows is None else None
+    if hit is None:                              # reference path: torch.rand in row chunks
+        if chunk_rows is None:
+            chunk_rows = max(1, min(n, (1 << 24) // max(n, 1)))
+        hits = []
+        for r0 in range(0, n, chunk_rows):
+            r1 = min(n, r0 + chunk_rows)
+            nz = (torch.rand(size=(r1 - r0, n)) < thr).nonzero()
+            if nz.numel():
+                nz = nz.numpy()
+                hits.append((nz[:, 0].astype(np.int64) + r0) * n + nz[:, 1])
+        hit = np.concatenate(hits) if hits else np.empty(0, dtype=np.int64)
     pos = np.ascontiguousarray(pos_indices.T)          # [E_L, 2] == adj.nonzero() order (697)
     np.random.shuffle(pos)                             # row shuffle (699)
     forced = pos[: e_l // 3]

@@ -276,6 +276,17 @@ int64_t edis_merge_pairs_host(int64_t n_hit, const int64_t* hit_key, int64_t n_f
                               const int64_t* forced_key, int64_t n_pos, const int64_t* pos_key,
                               int64_t* out_key, float* out_label);
 
+/* Bit-exact replay of `(torch.rand(n_draws) < thr).nonzero()` on torch's CPU generator without
+ * materialising the uniforms (pretrainer.py:692 / 559 draw N x N of them per call).  HOST pointers.
+ *   state   the 5056-byte blob of torch.get_rng_state() (CPUGeneratorImplState: mt19937 words,
+ *           `left`, `next`); advanced IN PLACE by n_draws outputs -- torch.set_rng_state(state)
+ *           then leaves the generator exactly where the reference's torch.rand would
+ *   thr24   ceil(float32(thr) * 2^24): a float32 uniform is (y & 0xFFFFFF) * 2^-24
+ *   out     ascending linear draw indices of the hits (k = i * N + j), capacity cap
+ * Returns the hit count, or -(count) if cap is too small (state untouched), or an EDIS_ERR_*. */
+int64_t edis_rand_hits_host(uint8_t* state, int64_t state_bytes, int64_t n_draws, uint32_t thr24,
+                            int64_t* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

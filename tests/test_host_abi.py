@@ -125,3 +125,24 @@ def test_sampler_cora():
     pairs, lab = sample_pairs(n, idx)
     assert pairs.shape[1] == int(g["cora_sample_m"])
     assert sha(pairs) == str(g["cora_sample_idx_sha"]) and sha(lab) == str(g["cora_sample_lab_sha"])
+
+
+@pytest.mark.parametrize("seed,n,thr", [(0, 1000, 0.013), (4, 3001, 0.00217), (11, 50, 0.5), (3, 700, 1e-9),
+                                        (5, 333, 1.0), (9, 1, 0.3)])
+def test_rand_hits_replays_torch_cpu_generator_bit_exactly(seed, n, thr):
+    """edis_rand_hits_host == (torch.rand(N, N) < thr).nonzero() on the CPU default generator,
+    hit for hit, and leaves the generator in the same state (the reference samples its SSL pairs
+    from exactly this stream, pretrainer.py:692)."""
+    import numpy as np
+    import torch
+    from edgedisentangle_ssl_b200.sampler import bernoulli_hits
+    torch.manual_seed(seed)
+    torch.rand(seed * 7 + 3)                      # start in the middle of a 624-word block
+    st0 = torch.get_rng_state().clone()
+    ref = (torch.rand(size=(n, n)) < thr).nonzero()
+    ref_key = (ref[:, 0] * n + ref[:, 1]).numpy()
+    after_ref = torch.rand(7)
+    torch.set_rng_state(st0)
+    got = bernoulli_hits(n * n, thr)
+    assert got is not None and np.array_equal(got, ref_key)
+    assert torch.equal(torch.rand(7), after_ref)
