@@ -144,6 +144,7 @@ def cora_full_epoch_ms():
             "--constrain_layer=0", "--epochs=4", "--gnn_type=AT"]
     out = {}
     for name, env in (("reference_rng_sampler_sklearn", {"EDIS_SAMPLER": "exact", "EDIS_HOST_METRICS": "1"}),
+                      ("reference_rng_sampler_device_metrics", {"EDIS_SAMPLER": "exact", "EDIS_HOST_METRICS": "device"}),
                       ("device_sampler_sklearn", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "1"}),
                       ("device_sampler_device_metrics", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "device"}),
                       ("device_sampler_no_metrics", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "0"})):
@@ -160,8 +161,9 @@ def cora_full_epoch_ms():
                 else:
                     os.environ[k] = v
     out["note"] = ("rows: SSL pair sampler (exact = the reference's CPU RNG stream replayed bit for bit, O(N^2) "
-                   "uniforms per draw; device = same law in O(M) on the GPU) x validation AUC / macro-F1 per CLS "
-                   "step (sklearn on host copies like the reference / computed on the device / dropped).  "
+                   "MT19937 outputs per draw, edis_rand_hits_host; device = same law in O(M) on the GPU) x validation "
+                   "AUC / macro-F1 per CLS step (sklearn on host copies like the reference / computed on the device / "
+                   "dropped).  reference_rng_sampler_device_metrics is the package default at this size.  "
                    "cora_full N=19793 E=146635, synthetic 64-d features (the feature blob is missing from the "
                    "reference snapshot); epoch 1 (graph build, warm-up) excluded; the reference's CPU path "
                    "took ~49 s per epoch in the survey probe (BASELINE.md)")
