@@ -97,14 +97,12 @@ extern "C" int64_t edis_build_adjacency_host(int64_t n, int64_t m, const int64_t
     set_error("edis_build_adjacency_host: bad arguments");
     return EDIS_ERR_ARG;
   }
-  // directed records: original orientation (flag 1) + mirrored (flag 2); diagonal handled apart
-  std::vector<int64_t> R, Cc;
-  std::vector<double> V;
-  std::vector<uint8_t> Fl;
-  R.reserve(2 * m);
-  Cc.reserve(2 * m);
-  V.reserve(2 * m);
-  Fl.reserve(2 * m);
+  // Row buckets instead of a global sort: pass 1 validates and counts the directed records per row
+  // (every off-diagonal entry (r, c) contributes (r, c) with flag 1 and its mirror (c, r) with flag
+  // 2; np.fill_diagonal overwrites the diagonal, data_load.py:69), pass 2 scatters (col, value,
+  // flag) into the row's bucket, pass 3 sorts each (short) bucket by column and merges duplicates.
+  // Sequential reads, one scattered write per record, no permutation gathers.
+  std::vector<int64_t> ptr(n + 1, 0);
   for (int64_t k = 0; k < m; ++k) {
     const int64_t r = rows[k], c = cols[k];
     if (r < 0 || r >= n || c < 0 || c >= n) {
@@ -112,59 +110,73 @@ extern "C" int64_t edis_build_adjacency_host(int64_t n, int64_t m, const int64_t
                 (long long)k, (long long)r, (long long)c, (long long)n);
       return EDIS_ERR_ARG;
     }
-    if (r == c) continue;  // np.fill_diagonal(adj, 1) overwrites the diagonal (data_load.py:69)
-    const double v = vals ? vals[k] : 1.0;
-    R.push_back(r); Cc.push_back(c); V.push_back(v); Fl.push_back(1);
-    R.push_back(c); Cc.push_back(r); V.push_back(v); Fl.push_back(2);
+    if (r == c) continue;
+    ++ptr[r + 1];
+    ++ptr[c + 1];
   }
-  const int64_t len = static_cast<int64_t>(R.size());
-  std::vector<int64_t> o1(len), o2(len), cnt;
-  counting_order(n, len, Cc.data(), nullptr, o1.data(), cnt);
-  counting_order(n, len, R.data(), o1.data(), o2.data(), cnt);
-  // dedup: value = max(A_ij, A_ji) with absent = 0 (data_load.py:71), then drop zeros
-  std::vector<int64_t> ur, uc;
-  std::vector<double> uv;
-  ur.reserve(len / 2 + n);
-  uc.reserve(len / 2 + n);
-  uv.reserve(len / 2 + n);
-  std::vector<double> deg(n, 0.0);
-  int64_t k = 0;
-  int64_t next_diag = 0;  // diagonal entries are merged in row-major position
-  auto emit_diag_upto = [&](int64_t row_limit, int64_t col_limit) {
-    // emit (d, d) for all pending d with (d,d) < (row_limit, col_limit) in row-major order
-    while (next_diag < n && (next_diag < row_limit || (next_diag == row_limit && next_diag < col_limit))) {
-      ur.push_back(next_diag); uc.push_back(next_diag); uv.push_back(1.0);
-      deg[next_diag] += 1.0;
-      ++next_diag;
-    }
+  for (int64_t r = 0; r < n; ++r) ptr[r + 1] += ptr[r];
+  const int64_t len = ptr[n];
+  struct Rec {
+    int64_t col;
+    double v;
+    uint8_t fl;
   };
-  while (k < len) {
-    const int64_t r = R[o2[k]], c = Cc[o2[k]];
-    double best = V[o2[k]];
-    uint8_t fl = Fl[o2[k]];
-    int64_t k2 = k + 1;
-    while (k2 < len && R[o2[k2]] == r && Cc[o2[k2]] == c) {
-      best = std::max(best, V[o2[k2]]);
-      fl |= Fl[o2[k2]];
-      ++k2;
+  std::vector<Rec> rec(static_cast<size_t>(len));
+  {
+    std::vector<int64_t> pos(ptr.begin(), ptr.end() - 1);
+    for (int64_t k = 0; k < m; ++k) {
+      const int64_t r = rows[k], c = cols[k];
+      if (r == c) continue;
+      const double v = vals ? vals[k] : 1.0;
+      rec[pos[r]++] = {c, v, 1};
+      rec[pos[c]++] = {r, v, 2};
     }
-    if (fl != 3) best = std::max(best, 0.0);  // the other orientation is an implicit 0
-    if (best != 0.0) {
-      emit_diag_upto(r, c);
-      ur.push_back(r); uc.push_back(c); uv.push_back(best);
-      deg[r] += best;
-    }
-    k = k2;
   }
-  emit_diag_upto(n, 0);
-  const int64_t E = static_cast<int64_t>(ur.size());
-  for (int64_t q = 0; q < E; ++q) {
+  // dedup: value = max(A_ij, A_ji) with absent = 0 (data_load.py:71), then drop zeros; the diagonal
+  // (value 1) is merged at its row-major position; rows are normalised by their sum in emission order
+  int64_t E = 0;
+  for (int64_t r = 0; r < n; ++r) {
+    Rec* b = rec.data() + ptr[r];
+    Rec* e = rec.data() + ptr[r + 1];
+    std::sort(b, e, [](const Rec& x, const Rec& y) { return x.col < y.col; });
+    double deg = 0.0;
+    bool diag_done = false;
+    // unique columns + merged values, compacted in place (the write index never overtakes the read index)
+    Rec* w = b;
+    for (Rec* q = b; q < e;) {
+      const int64_t c = q->col;
+      double best = q->v;
+      uint8_t fl = q->fl;
+      for (++q; q < e && q->col == c; ++q) {
+        best = std::max(best, q->v);
+        fl |= q->fl;
+      }
+      if (fl != 3) best = std::max(best, 0.0);   // the other orientation is an implicit 0
+      if (best != 0.0) *w++ = {c, best, fl};
+    }
+    // row sum in row-major order with the diagonal in place
+    for (Rec* q = b; q < w; ++q) {
+      if (!diag_done && q->col > r) {
+        deg += 1.0;
+        diag_done = true;
+      }
+      deg += q->v;
+    }
+    if (!diag_done) deg += 1.0;
     // normalize_adj (data_load.py:12-20): r_inv = rowsum**-1 (inf -> 0), values r_inv * a (float64)
-    double rinv = std::pow(deg[ur[q]], -1.0);
+    double rinv = std::pow(deg, -1.0);
     if (std::isinf(rinv)) rinv = 0.0;
-    out_row[q] = ur[q];
-    out_col[q] = uc[q];
-    out_val[q] = static_cast<float>(rinv * uv[q]);
+    diag_done = false;
+    for (Rec* q = b; q < w; ++q) {
+      if (!diag_done && q->col > r) {
+        out_row[E] = r; out_col[E] = r; out_val[E] = static_cast<float>(rinv * 1.0); ++E;
+        diag_done = true;
+      }
+      out_row[E] = r; out_col[E] = q->col; out_val[E] = static_cast<float>(rinv * q->v); ++E;
+    }
+    if (!diag_done) {
+      out_row[E] = r; out_col[E] = r; out_val[E] = static_cast<float>(rinv * 1.0); ++E;
+    }
   }
   return E;
 }
