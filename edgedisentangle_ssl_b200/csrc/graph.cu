@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstring>
 #include <numeric>
+#include <thread>
 #include <vector>
 
 #include "edis_common.cuh"
@@ -394,6 +395,27 @@ extern "C" int64_t edis_merge_pairs_host(int64_t n_hit, const int64_t* hit_key, 
 // Returns the number of hits, or -(hits needed) if cap is too small (state untouched then).
 // The engine is ATen's mt19937 (ATen/core/MT19937RNGEngine.h): standard MT19937, `left` counts
 // the outputs remaining in the current 624-word block, regenerated when --left == 0.
+namespace {
+inline uint32_t temper24(uint32_t y) {
+  y ^= (y >> 11);
+  y ^= (y << 7) & 0x9d2c5680u;
+  y ^= (y << 15) & 0xefc60000u;
+  y ^= (y >> 18);
+  return y & 0xFFFFFFu;
+}
+// hits among the raw MT words w[0, cnt): draw index base + t for every t with temper24(w[t]) < thr24
+void scan_words(const uint32_t* w, int64_t cnt, int64_t base, uint32_t thr24, std::vector<int64_t>* hits) {
+  constexpr int B = 1024;
+  uint32_t tmp[B];
+  for (int64_t o = 0; o < cnt; o += B) {
+    const int len = static_cast<int>(std::min<int64_t>(B, cnt - o));
+    for (int t = 0; t < len; ++t) tmp[t] = temper24(w[o + t]);      // vectorises
+    for (int t = 0; t < len; ++t)
+      if (tmp[t] < thr24) hits->push_back(base + o + t);            // rare
+  }
+}
+}  // namespace
+
 extern "C" int64_t edis_rand_hits_host(uint8_t* state, int64_t state_bytes, int64_t n_draws,
                                        uint32_t thr24, int64_t* out, int64_t cap) {
   if (!state || state_bytes < 24 + 624 * 8 || n_draws < 0 || (!out && cap > 0)) {
@@ -412,44 +434,73 @@ extern "C" int64_t edis_rand_hits_host(uint8_t* state, int64_t state_bytes, int6
     mt[i] = static_cast<uint32_t>(v);
   }
   uint32_t next = static_cast<uint32_t>(next64);
-  auto twist = [](uint32_t u, uint32_t v) {
-    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((v & 1u) ? 0x9908b0dfu : 0u);
-  };
-  auto regenerate = [&]() {
-    uint32_t* p = mt;
-    for (int j = N - M + 1; --j; ++p) *p = p[M] ^ twist(p[0], p[1]);
-    for (int j = M; --j; ++p) *p = p[M - N] ^ twist(p[0], p[1]);
-    *p = p[M - N] ^ twist(p[0], mt[0]);
-    left = N;
-    next = 0;
-  };
-  int64_t hits = 0, k = 0;
-  while (k < n_draws) {
-    if (--left == 0) regenerate();
-    // outputs available without another regeneration: this one plus (left - 1) more
-    const int64_t run = std::min<int64_t>(n_draws - k, static_cast<int64_t>(left));
-    // two phases so that the tempering vectorises: temper a block, then scan it for the (rare) hits
-    uint32_t tmp[N];
-    const uint32_t* src = mt + next;
-    for (int t = 0; t < static_cast<int>(run); ++t) {
-      uint32_t y = src[t];
-      y ^= (y >> 11);
-      y ^= (y << 7) & 0x9d2c5680u;
-      y ^= (y << 15) & 0xefc60000u;
-      y ^= (y >> 18);
-      tmp[t] = y & 0xFFFFFFu;
-    }
-    for (int t = 0; t < static_cast<int>(run); ++t) {
-      if (tmp[t] < thr24) {
-        if (hits < cap) out[hits] = k + t;
-        ++hits;
-      }
-    }
-    next += static_cast<uint32_t>(run);
-    left -= static_cast<int32_t>(run - 1);
-    k += run;
+  if (left < 1 || left > N || next > static_cast<uint32_t>(N)) {
+    set_error("edis_rand_hits_host: implausible generator state (left=%d next=%u)", left, next);
+    return EDIS_ERR_ARG;
   }
-  if (hits > cap) return -hits;
+  auto twist = [](uint32_t u, uint32_t v) {
+    return (((u & 0x80000000u) | (v & 0x7fffffffu)) >> 1) ^ ((0u - (v & 1u)) & 0x9908b0dfu);
+  };
+  // next block `nw` from the previous one `old` (MT19937RNGEngine.h next_state(), written out of
+  // place: no load/store hazards, so the three loops vectorise)
+  auto next_block = [&](const uint32_t* __restrict__ old, uint32_t* __restrict__ nw) {
+    for (int i = 0; i < N - M; ++i) nw[i] = old[i + M] ^ twist(old[i], old[i + 1]);
+    // nw[i] needs nw[i - 227]: independent within runs of 227, done as two such runs
+    for (int i = N - M; i < 2 * (N - M); ++i) nw[i] = nw[i + M - N] ^ twist(old[i], old[i + 1]);
+    for (int i = 2 * (N - M); i < N - 1; ++i) nw[i] = nw[i + M - N] ^ twist(old[i], old[i + 1]);
+    nw[N - 1] = nw[M - 1] ^ twist(old[N - 1], nw[0]);
+  };
+  // ATen's engine: a draw does `if (--left == 0) regenerate (left = 624, next = 0)` and then takes
+  // mt[next++].  So left - 1 words of the current block are still unread, starting at mt[next].
+  std::vector<int64_t> hits;
+  int64_t k = 0;
+  {
+    const int64_t a0 = std::min<int64_t>(n_draws, left - 1);
+    scan_words(mt + next, a0, 0, thr24, &hits);
+    next += static_cast<uint32_t>(a0);
+    left -= static_cast<int32_t>(a0);
+    k = a0;
+  }
+  // Whole blocks: the recurrence is sequential (this thread), tempering + threshold test is not:
+  // blocks are generated into one half of a double buffer while helper threads scan the other half.
+  constexpr int64_t kChunkBlocks = 2048;                           // 2048 * 624 words = 5 MB per half
+  const int helpers = static_cast<int>(std::max(1u, std::min(4u, std::thread::hardware_concurrency() > 1
+                                                                      ? std::thread::hardware_concurrency() - 1 : 1u)));
+  std::vector<uint32_t> buf[2];
+  std::vector<std::thread> workers;
+  std::vector<std::vector<int64_t>> part(helpers);
+  auto drain = [&]() {
+    for (auto& t : workers) t.join();
+    workers.clear();
+    for (auto& p : part) {
+      hits.insert(hits.end(), p.begin(), p.end());
+      p.clear();
+    }
+  };
+  int half = 0;
+  while (k < n_draws) {
+    const int64_t want = std::min<int64_t>(n_draws - k, kChunkBlocks * N);
+    const int64_t blocks = (want + N - 1) / N;
+    std::vector<uint32_t>& b = buf[half];
+    b.resize(static_cast<size_t>(blocks) * N);
+    for (int64_t q = 0; q < blocks; ++q) next_block(q ? b.data() + (q - 1) * N : mt, b.data() + q * N);
+    std::memcpy(mt, b.data() + (blocks - 1) * N, sizeof(mt));
+    const int64_t last = want - (blocks - 1) * N;                  // words consumed from the last block
+    left = N + 1 - static_cast<int32_t>(last);
+    next = static_cast<uint32_t>(last);
+    drain();                                                       // the other half is free again
+    const int64_t per = (want + helpers - 1) / helpers;
+    for (int h = 0; h < helpers; ++h) {
+      const int64_t lo = std::min<int64_t>(want, h * per), hi = std::min<int64_t>(want, lo + per);
+      if (hi > lo) workers.emplace_back(scan_words, b.data() + lo, hi - lo, k + lo, thr24, &part[h]);
+    }
+    k += want;
+    half ^= 1;
+  }
+  drain();
+  const int64_t nh = static_cast<int64_t>(hits.size());
+  if (nh > cap) return -nh;
+  if (nh) std::memcpy(out, hits.data(), static_cast<size_t>(nh) * sizeof(int64_t));
   std::memcpy(state + 8, &left, 4);
   next64 = next;
   std::memcpy(state + 16, &next64, 8);
@@ -457,5 +508,5 @@ extern "C" int64_t edis_rand_hits_host(uint8_t* state, int64_t state_bytes, int6
     const uint64_t v = mt[i];
     std::memcpy(state + 24 + 8 * i, &v, 8);
   }
-  return hits;
+  return nh;
 }
