@@ -223,6 +223,20 @@ def _edge_indices_host(adj):
     return g.n, np.stack([row, ex["col"].astype(np.int64)])
 
 
+def disedge_label_sets(n, idx, labels, conform_t=False, node_sup_ratio=0.25):
+    """DisEdge supervision as two edge lists [2, E_k] (same-label edges, different-label edges) of
+    the adjacency `idx` [2, E] (row-major); host-side, no N x N (pretrainer.py:440-456).
+    conform_t ("real setting", pretrainer.py:466-506): only edges between two nodes whose labels are
+    KNOWN -- the train + validation part of a fresh `utils.split`, which consumes python's RNG exactly
+    like the reference's call -- take part."""
+    if conform_t:
+        idx_train, idx_val, _, _ = utils.split(labels, train_ratio=node_sup_ratio)
+        known = np.zeros(n, dtype=bool)
+        known[torch.cat((idx_train, idx_val), dim=-1).numpy()] = True
+        idx = idx[:, known[idx[0]] & known[idx[1]]]
+    return homo_hetero_split(idx, labels.numpy())
+
+
 class _PairTrainer(Trainer):
     """Shared machinery of SupEdge / DisEdge: sample pairs, score them, fused weighted MSE."""
 
@@ -327,12 +341,10 @@ class GeneratedEdgeTrainer(_PairTrainer):
         super().__init__(args, model, weight)
         self.dis_type = args.dis_type
         assert self.dis_type == 1, "currently only use homo&hetero edge disentanglement"
-        if args.conformT:
-            raise NotImplementedError("--conformT (pretrainer.py:466-506) is listed under 'next' in SURVEY 8(f)")
 
     def get_label_all(self, feature, adj, labels, load=True):
         n, idx = _edge_indices_host(adj)
-        homo, het = homo_hetero_split(idx, labels.cpu().numpy())
+        homo, het = disedge_label_sets(n, idx, labels.cpu(), self.args.conformT, self.args.node_sup_ratio)
         for i, s in enumerate((homo, het)):
             print("edge group {} for edge disentanglement SSL size: {}".format(i, float(s.shape[1])))
         self.labels_ssl = EdgeLabels(n, [homo, het])

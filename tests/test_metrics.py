@@ -59,3 +59,31 @@ def test_fuse_layer_variants_match_reference_golden(rt, use_res, no_relu):
     # the channel-fused [N, C*D] tensor is accepted directly (the cat is free on the B200 path)
     y2 = f(torch.cat([t.detach() for t in x], 1), r if use_res else None)
     assert torch.allclose(y2, y.detach(), rtol=0, atol=0)
+
+
+def test_disedge_conformt_label_sets_match_reference_golden():
+    """--conformT (pretrainer.py:466-506): homo / hetero edge sets restricted to edges between
+    label-known nodes, bit-exact with the unmodified reference on bundled chameleon, including the
+    position it leaves python's RNG at (tests/golden/make_golden_conformt.py).  Host-side logic."""
+    import contextlib
+    import io
+    import os
+    import random
+    import numpy as np
+    from edgedisentangle_ssl_b200 import data_load, utils
+    from edgedisentangle_ssl_b200.trainer import disedge_label_sets
+    here = os.path.dirname(os.path.abspath(__file__))
+    g = np.load(os.path.join(here, "golden", "conformt_chameleon.npz"))
+    args = utils.get_parser().parse_args(["--model=DISGAT", "--sparse", "--dataset=chameleon", "--conformT"])
+    args.hetero = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        adj, _, labels = data_load.load_data(args, path=os.path.join(os.path.dirname(here), "data", "chameleon") + "/",
+                                             dataset="chameleon", edge_type=1)
+        idx = adj.coalesce().indices().numpy()
+        random.seed(11)
+        homo, het = disedge_label_sets(adj.shape[0], idx, labels, True, args.node_sup_ratio)
+    assert np.array_equal(homo, g["set0"]) and np.array_equal(het, g["set1"])
+    assert random.random() == float(g["py_random_after"])
+    # without --conformT every edge takes part (pretrainer.py:440-456)
+    homo_all, het_all = disedge_label_sets(adj.shape[0], idx, labels, False)
+    assert homo_all.shape[1] + het_all.shape[1] == idx.shape[1]
