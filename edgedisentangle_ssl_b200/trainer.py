@@ -130,6 +130,32 @@ class Trainer(object):
     def get_em(self, feature, adj):
         return fuse_feature(self.models[0].get_em(feature, adj, self.fusers), fuse=self.args.fuse)
 
+    def analyze_disentangle(self, feature, adj):
+        """--case study (trainer.py:82-134): how correlated are the channels' attention logits and the
+        embedding dimensions?  Pairs are sampled exactly like SupEdge's `sample_train` (same RNG
+        pattern; edge lists instead of the dense N x N mask), scored by every channel of both layers,
+        and correlated.  Returns (at_distance_list[2], at_cor_graph_lists[2] of [C, C],
+        feat_cor_graph_lists[2] of [nhid, nhid])."""
+        assert self.args.model == "DISGAT", "analyze disentanglement is only implemented for DISGAT"
+        from .sampler import sample_pairs, sample_pairs_device
+        feats = self.models[0].get_em(feature, adj, self.fusers)
+        n, idx = _edge_indices_host(adj)
+        dev = feature.device
+        mode = os.environ.get("EDIS_SAMPLER") or ("exact" if n <= 50_000 else "device")
+        if mode == "exact":
+            pairs = torch.from_numpy(sample_pairs(n, idx)[0]).to(dev)
+        else:
+            pairs = sample_pairs_device(n, torch.from_numpy(idx[0] * n + idx[1]).to(dev))[0]
+        adjs = self.models[0].predict_adjs_sparse(feature, adj, self.fusers, auxiliary_edges=pairs)
+        at_distance_list, at_cor_graph_lists, feat_cor_graph_lists = [], [], []
+        for layer in range(2):
+            feat_cor_graph_lists.append(utils.group_correlation(feats[layer].transpose(0, 1)))
+            adj_layer = torch.stack([a[0] for a in adjs[layer]]).squeeze(-1)          # [C, M]
+            cor = utils.group_correlation(adj_layer)
+            at_cor_graph_lists.append(cor)
+            at_distance_list.append(torch.mean(torch.abs(cor)).item())
+        return at_distance_list, at_cor_graph_lists, feat_cor_graph_lists
+
     def reg_fuser(self):
         """L1 norm of the fuser weights (trainer.py:136-142)."""
         l1 = sum(p.abs().sum() for p in self.fuse1.parameters()) + sum(p.abs().sum() for p in self.fuse2.parameters())

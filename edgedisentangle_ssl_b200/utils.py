@@ -100,6 +100,14 @@ def adj_mse_loss(adj_rec, adj_tgt):
     return Fn.SslWmse.apply(logits, adj_tgt.reshape(-1), n_pos)
 
 
+def group_correlation(embedding):
+    """Pearson correlation between the ROWS of `embedding` [G, n] -> [G, G] (utils.py:326-334), with
+    the norms taken from the centred rows directly instead of the diagonal of a G x G product."""
+    x = embedding - embedding.mean(dim=-1, keepdim=True)
+    nrm = torch.sqrt((x * x).sum(-1))
+    return (x @ x.t()) / torch.outer(nrm, nrm)
+
+
 def accuracy(output, labels):
     preds = output.max(1)[1].type_as(labels)
     return preds.eq(labels).double().sum() / len(labels)

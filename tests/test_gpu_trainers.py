@@ -238,3 +238,36 @@ def test_checkpoint_round_trip_resumes_bit_exactly(tmp_path):
     resumed = torch.load(M.checkpoint_path(args, 0, str(tmp_path))[1], map_location="cpu")
     moved = max(float((resumed["encoder"][k] - v).abs().max()) for k, v in saved["encoder"].items())
     assert 0.0 < moved < 0.1          # one more epoch of Adam steps from the loaded state, not a re-init
+
+
+def test_case_study_matches_reference_golden():
+    """`Trainer.analyze_disentangle` (--case, trainer.py:82-134): same sampled pairs (RNG stream
+    replayed), same channel / feature correlation maps as the unmodified reference
+    (tests/golden/make_golden_case.py), eval mode."""
+    g, c = load("model_a3_AT"), load("case_a3_AT")
+    args = get_parser().parse_args([str(a) for a in g["argv"]])
+    args.cuda, args.hetero, args.edge_num = True, True, 1
+    args.size = g["x"].shape[1]
+    x, labels = t(g["x"]).to(DEV), t(g["labels"]).to(DEV)
+    args.nclass = int(labels.max()) + 1
+    n = int(g["n"])
+    idx = torch.as_tensor(g["indices"])
+    adj = torch.sparse_coo_tensor(idx, torch.ones(idx.shape[1]), (n, n)).to(DEV)
+    seed_all(4)
+    enc = edis.DISGAT(args, nfeat=args.size, nhid=args.nhid, nclass=args.nhid, nheads=args.nhead,
+                      dropout=args.dropout).to(DEV)
+    cls = T.ClsTrainer(args, enc, labels, 1.0)
+    load_into(enc, g, "enc0.")
+    load_into(cls.fuse1, g, "cls0.fuse1.")
+    load_into(cls.fuse2, g, "cls0.fuse2.")
+    for m in cls.models:
+        m.eval()
+    torch.manual_seed(21)
+    np.random.seed(21)
+    with torch.no_grad():
+        dist, at_cor, feat_cor = cls.analyze_disentangle(x, adj)
+    assert torch.equal(torch.rand(3), t(c["torch_rand_after"]))          # consumed the same RNG stream
+    for layer in range(2):
+        assert abs(dist[layer] - float(c["at_distance"][layer])) < 1e-5
+        assert_close(at_cor[layer].cpu(), t(c["at_cor%d" % layer]), 2e-5, "at_cor%d" % layer)
+        assert_close(feat_cor[layer].cpu(), t(c["feat_cor%d" % layer]), 2e-5, "feat_cor%d" % layer)

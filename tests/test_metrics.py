@@ -87,3 +87,12 @@ def test_disedge_conformt_label_sets_match_reference_golden():
     # without --conformT every edge takes part (pretrainer.py:440-456)
     homo_all, het_all = disedge_label_sets(adj.shape[0], idx, labels, False)
     assert homo_all.shape[1] + het_all.shape[1] == idx.shape[1]
+
+
+def test_group_correlation_is_pearson_between_rows():
+    """utils.group_correlation (utils.py:326-334) == numpy's corrcoef of the rows."""
+    import numpy as np
+    from edgedisentangle_ssl_b200.utils import group_correlation
+    torch.manual_seed(3)
+    e = torch.randn(7, 400, dtype=torch.float64)
+    assert np.allclose(group_correlation(e).numpy(), np.corrcoef(e.numpy()), atol=1e-12)
