@@ -935,6 +935,10 @@ static void fill_common(LayerArgs& A, const edis_layer_desc* d, const float* P, 
 }
 
 static int check_ws(const edis_graph* g, int64_t pw, void* workspace, int64_t bytes, const char* who) {
+  if (g->device < 0) {
+    set_error("%s: structure-only graph handle (created with device -1): nothing is resident on a GPU", who);
+    return EDIS_ERR_ARG;
+  }
   if ((g->dst.n_slots > 0 || g->src.n_slots > 0) &&
       (!workspace || bytes < edis_graph_workspace_bytes(g, pw))) {
     set_error("%s: workspace too small (%lld < %lld)", who, (long long)bytes,

@@ -261,6 +261,14 @@ extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, c
   }
   std::vector<Item> items;
   std::vector<SplitRow> split;
+  if (device < 0) {
+    // structure-only handle (device == -1): host mirrors and schedules, nothing uploaded.  For
+    // edis_graph_info / edis_graph_export (host-side checks of the builder); every op rejects it.
+    g->dst = build_schedule_host(n, g->h_rowptr, max_chunk, items, split);
+    g->src = build_schedule_host(n_cols, g->h_cscptr, max_chunk, items, split);
+    *out = g;
+    return EDIS_OK;
+  }
   int prev_dev = 0;
   cudaGetDevice(&prev_dev);
   int rc = EDIS_OK;
@@ -314,8 +322,10 @@ extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, c
 
 extern "C" void edis_graph_destroy(edis_graph* g) {
   if (!g) return;
+  if (g->device >= 0) {
   cudaFree(g->rowptr); cudaFree(g->col); cudaFree(g->cscptr); cudaFree(g->cscrow); cudaFree(g->csceid);
   cudaFree(g->dst.items); cudaFree(g->dst.split); cudaFree(g->src.items); cudaFree(g->src.split);
+  }
   delete[] g->h_rowptr; delete[] g->h_col; delete[] g->h_perm;
   delete[] g->h_cscptr; delete[] g->h_cscrow; delete[] g->h_csceid;
   delete g;

@@ -56,7 +56,10 @@ int64_t edis_build_adjacency_host(int64_t n, int64_t m, const int64_t* rows, con
  *               duplicate-free it is sorted (stable) and `perm` reports the permutation.
  *   max_chunk   max edges one warp processes for one row (rows above are split); 0 = default
  * The CSR edge order equals the reference's coalesced order, so edge tensors line up with
- * the reference's `edge_e[k]` with no permutation. */
+ * the reference's `edge_e[k]` with no permutation.
+ *   device      CUDA device ordinal, or -1 for a STRUCTURE-ONLY handle: host mirrors and schedules
+ *               are built, nothing is uploaded; usable with edis_graph_info / edis_graph_export only
+ *               (host-side checks of the builder) -- every op rejects it. */
 typedef struct edis_graph edis_graph;
 int edis_graph_create(int64_t n, int64_t e, const int64_t* row, const int64_t* col, int max_chunk,
                       int device, edis_graph** out);
