@@ -152,3 +152,45 @@ def test_ops_reject_a_structure_only_handle():
     rc = lib.edis_disga_fwd(g.h, ctypes.byref(d), one, 128, one, 128, one, one, 128, None, one, one, one, one, None,
                             one, 1 << 20, None)
     assert rc < 0 and "structure-only" in _lib.last_error()
+
+
+def test_edge_cases_empty_single_row_and_bad_input():
+    g = HostGraph(5, np.zeros(0, np.int64), np.zeros(0, np.int64))          # no edges at all
+    assert g.info["e"] == 0 and np.array_equal(g.rowptr, np.zeros(6, np.int64)) and g.info["dst_slots"] == 0
+    g = HostGraph(1, [0], [0])                                              # one node, one self loop
+    assert g.info["e"] == 1 and g.info["max_in"] == 1 and g.col[0] == 0
+    n = 300                                                                 # every edge in ONE row / ONE column
+    g = HostGraph(n, np.full(n, 7), np.arange(n), max_chunk=16)
+    assert g.info["max_in"] == n and g.info["dst_slots"] == -(-n // 16) and g.info["max_out"] == 1
+    check_csc(g)
+    h = ctypes.c_void_p()
+    bad = np.array([0, 5], dtype=np.int64)
+    rc = lib.edis_graph_create_rect(3, 3, 2, np_ptr(bad, ctypes.c_int64), np_ptr(bad, ctypes.c_int64), 0, -1,
+                                    ctypes.byref(h))
+    assert rc < 0 and "out of range" in _lib.last_error()
+    rc = lib.edis_graph_create_rect(3, 2, 0, None, None, 0, -1, ctypes.byref(h))   # n_cols < n_rows
+    assert rc < 0
+
+
+def test_adjacency_builder_edge_cases():
+    """edis_build_adjacency_host (data_load.py:39-77): empty edge list -> identity; duplicates keep
+    the max; an explicit zero-valued entry and a negative one vanish under max(A, A^T) >= 0; the
+    diagonal is overwritten with 1 before the row normalisation."""
+    from edgedisentangle_ssl_b200.graph import build_adjacency
+    idx, val = build_adjacency(4, np.zeros(0, np.int64), np.zeros(0, np.int64))
+    assert np.array_equal(idx, np.stack([np.arange(4)] * 2)) and np.allclose(val, 1.0)
+    rows = np.array([0, 0, 1, 2, 2, 3], dtype=np.int64)
+    cols = np.array([1, 1, 0, 3, 2, 0], dtype=np.int64)
+    vals = np.array([0.5, 2.0, 1.0, 0.0, 9.0, -1.0])
+    idx, val = build_adjacency(4, rows, cols, vals)
+    dense = np.zeros((4, 4))                                                # the reference's dense recipe
+    seen = set()
+    for r, c, v in zip(rows, cols, vals):
+        dense[r, c] = max(dense[r, c], v) if (r, c) in seen else v          # duplicates keep the max
+        seen.add((r, c))
+    np.fill_diagonal(dense, 1)                                              # data_load.py:69
+    dense = np.maximum(dense, dense.T)                                      # data_load.py:71
+    dense = dense / dense.sum(1, keepdims=True)                             # normalize_adj
+    got = np.zeros((4, 4))
+    got[idx[0], idx[1]] = val
+    assert np.allclose(got, dense, atol=1e-7) and np.count_nonzero(got) == idx.shape[1]
