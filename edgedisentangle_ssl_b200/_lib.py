@@ -23,6 +23,7 @@ class LayerDesc(Structure):
                 ("reserved", c_int32)]
 
 
+ERR_STALE = -5
 FLAG_PLAIN_MEAN = 1
 FLAG_NO_GX = 2
 FLAG_PHASE_DST, FLAG_PHASE_SRC, FLAG_PHASE_GX = 4, 8, 16
@@ -58,8 +59,12 @@ SIGNATURES = {
     "edis_graph_create_rect": (c_int, [c_int64, c_int64, c_int64, _i64p, _i64p, c_int, c_int, POINTER(c_void_p)]),
     "edis_graph_destroy": (None, [c_void_p]),
     "edis_graph_info": (c_int, [c_void_p, _i64p]),
+    "edis_graph_input_entries": (c_int64, [c_void_p]),
     "edis_graph_export": (c_int, [c_void_p, _i64p, _i32p, _i64p, _i64p, _i32p, _i32p]),
     "edis_graph_workspace_bytes": (c_int64, [c_void_p, c_int64]),
+    "edis_edge_list_key": (c_uint64, [c_int64, c_int64, c_int64, _i64p, _i64p, c_int]),
+    "edis_graph_save": (c_int, [c_void_p, c_char_p, c_uint64]),
+    "edis_graph_load": (c_int, [c_char_p, c_uint64, c_int, c_int, c_int, POINTER(c_void_p)]),
     "edis_disga_fwd": (c_int, [c_void_p, _descp, _P, c_int64, _P, c_int64, _P, _P, c_int64, _P,
                                _P, _P, _P, _P, _P, _P, c_int64, _P]),
     "edis_disga_rec_bytes": (c_int64, [c_void_p, _descp]),

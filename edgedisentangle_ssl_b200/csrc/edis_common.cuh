@@ -66,6 +66,12 @@ struct edis_graph {
   int64_t* h_cscptr = nullptr;
   int32_t* h_cscrow = nullptr;
   int32_t* h_csceid = nullptr;
+  // host copies of the two schedules (edis_graph_save) and the chunk size they were built with
+  edis::Item* h_dst_items = nullptr;
+  edis::SplitRow* h_dst_split = nullptr;
+  edis::Item* h_src_items = nullptr;
+  edis::SplitRow* h_src_split = nullptr;
+  int max_chunk = 256;
 };
 
 namespace edis {

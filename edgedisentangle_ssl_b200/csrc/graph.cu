@@ -10,6 +10,11 @@
 #include <thread>
 #include <vector>
 
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include "edis_common.cuh"
 
 namespace edis {
@@ -192,8 +197,10 @@ extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, c
                                       const int64_t* col, int max_chunk, int device, edis_graph** out) {
   EDIS_CHECK_ARG(out && n > 0 && n_cols >= n && e_in >= 0 && (e_in == 0 || (row && col)),
                  "edis_graph_create: bad arguments (need n_cols >= n_rows > 0)");
-  EDIS_CHECK_ARG(e_in < (int64_t(1) << 31) - 64 && n_cols < (int64_t(1) << 31) - 64,
-                 "edis_graph_create: n and e must fit int32");
+  EDIS_CHECK_ARG(e_in < (int64_t(1) << 31) - 64, "edis_graph_create: e must fit int32");
+  // bits 30-31 of a device-side neighbour id carry its L2 heat level and every kernel masks them off
+  EDIS_CHECK_ARG(n_cols < (int64_t(1) << kHeatShift),
+                 "edis_graph_create: node ids must stay below 2^%d (got n_cols=%lld)", kHeatShift, (long long)n_cols);
   if (max_chunk <= 0) max_chunk = 256;
   bool sorted = true;
   for (int64_t k = 0; k < e_in; ++k) {
@@ -261,11 +268,20 @@ extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, c
   }
   std::vector<Item> items;
   std::vector<SplitRow> split;
+  g->max_chunk = max_chunk;
+  auto keep = [](const std::vector<Item>& it, const std::vector<SplitRow>& sp, Item** hi, SplitRow** hs) {
+    *hi = new Item[std::max<size_t>(it.size(), 1)];
+    *hs = new SplitRow[std::max<size_t>(sp.size(), 1)];
+    if (!it.empty()) memcpy(*hi, it.data(), it.size() * sizeof(Item));
+    if (!sp.empty()) memcpy(*hs, sp.data(), sp.size() * sizeof(SplitRow));
+  };
   if (device < 0) {
     // structure-only handle (device == -1): host mirrors and schedules, nothing uploaded.  For
     // edis_graph_info / edis_graph_export (host-side checks of the builder); every op rejects it.
     g->dst = build_schedule_host(n, g->h_rowptr, max_chunk, items, split);
+    keep(items, split, &g->h_dst_items, &g->h_dst_split);
     g->src = build_schedule_host(n_cols, g->h_cscptr, max_chunk, items, split);
+    keep(items, split, &g->h_src_items, &g->h_src_split);
     *out = g;
     return EDIS_OK;
   }
@@ -283,16 +299,18 @@ extern "C" int edis_graph_create_rect(int64_t n, int64_t n_cols, int64_t e_in, c
   }
   cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
   g->dst = build_schedule_host(n, g->h_rowptr, max_chunk, items, split);
+  keep(items, split, &g->h_dst_items, &g->h_dst_split);
   if ((rc = upload(&g->dst.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->dst.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
   g->src = build_schedule_host(n_cols, g->h_cscptr, max_chunk, items, split);
+  keep(items, split, &g->h_src_items, &g->h_src_split);
   if ((rc = upload(&g->src.items, items.data(), items.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->src.split, split.data(), split.size())) != EDIS_OK) return fail(rc);
   if ((rc = upload(&g->rowptr, g->h_rowptr, n + 1)) != EDIS_OK) return fail(rc);
   // device copies of the neighbour arrays carry the neighbour's heat level in bits 30-31
   // (see edis_common.cuh); the host mirrors stay plain
   std::vector<int32_t> dcol(g->h_col, g->h_col + e), dcscrow(g->h_cscrow, g->h_cscrow + e);
-  if (n_cols < (int64_t(1) << kHeatShift) && e > 0) {
+  if (e > 0) {
     auto heat_of = [](const int64_t* ptr, int64_t count) {
       std::vector<int64_t> deg(count);
       for (int64_t i = 0; i < count; ++i) deg[i] = ptr[i + 1] - ptr[i];
@@ -328,6 +346,7 @@ extern "C" void edis_graph_destroy(edis_graph* g) {
   }
   delete[] g->h_rowptr; delete[] g->h_col; delete[] g->h_perm;
   delete[] g->h_cscptr; delete[] g->h_cscrow; delete[] g->h_csceid;
+  delete[] g->h_dst_items; delete[] g->h_dst_split; delete[] g->h_src_items; delete[] g->h_src_split;
   delete g;
 }
 
@@ -341,6 +360,8 @@ extern "C" int edis_graph_info(const edis_graph* g, int64_t info[10]) {
   return EDIS_OK;
 }
 
+extern "C" int64_t edis_graph_input_entries(const edis_graph* g) { return g ? g->e_in : EDIS_ERR_ARG; }
+
 extern "C" int edis_graph_export(const edis_graph* g, int64_t* rowptr, int32_t* col, int64_t* perm,
                                  int64_t* cscptr, int32_t* cscrow, int32_t* csceid) {
   EDIS_CHECK_ARG(g, "edis_graph_export: null graph");
@@ -350,6 +371,241 @@ extern "C" int edis_graph_export(const edis_graph* g, int64_t* rowptr, int32_t* 
   if (cscptr) memcpy(cscptr, g->h_cscptr, (g->n_cols + 1) * sizeof(int64_t));
   if (cscrow) memcpy(cscrow, g->h_cscrow, g->e * sizeof(int32_t));
   if (csceid) memcpy(csceid, g->h_csceid, g->e * sizeof(int32_t));
+  return EDIS_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// On-disk graph cache: everything edis_graph_create derives from an edge list, in one
+// flat file that edis_graph_load memory-maps and uploads.  Replaces the reference's dense detour on
+// every start (data_load.py:39-77) and, being keyed by the caller's content hash, its stale
+// `./resource/<ds>/DisEdges.pt` hazard (pretrainer.py:390-398): a file written for other input, another
+// chunk size or another format version is rejected, never silently used.
+namespace {
+constexpr uint64_t kCacheMagic = 0x3147534944450a0dull;   // "\r\nEDISG1"
+constexpr uint32_t kCacheVersion = 2;
+struct CacheHeader {
+  uint64_t magic;
+  uint32_t version, max_chunk;
+  uint64_t key;
+  int64_t n, n_cols, e, e_in, max_in, max_out, was_sorted;
+  int64_t dst_items, dst_slots, dst_split, src_items, src_slots, src_split;
+  uint64_t payload_bytes, payload_hash;
+};
+inline uint64_t mix64(uint64_t h, uint64_t v) {
+  h ^= v + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+  h *= 0xff51afd7ed558ccdull;
+  return h ^ (h >> 32);
+}
+uint64_t hash_bytes(const void* p, size_t bytes, uint64_t seed) {
+  // 4 independent lanes over 8-byte words (memory-bound on one core: ~5 GB/s)
+  const uint64_t* w = static_cast<const uint64_t*>(p);
+  const size_t nw = bytes / 8;
+  uint64_t h[4] = {seed, seed ^ 0xa5a5a5a5a5a5a5a5ull, seed + 0x1234567ull, ~seed};
+  size_t i = 0;
+  for (; i + 4 <= nw; i += 4)
+    for (int k = 0; k < 4; ++k) h[k] = mix64(h[k], w[i + k]);
+  for (; i < nw; ++i) h[0] = mix64(h[0], w[i]);
+  uint64_t tail = 0;
+  memcpy(&tail, static_cast<const uint8_t*>(p) + nw * 8, bytes - nw * 8);
+  uint64_t r = mix64(h[0], tail);
+  for (int k = 1; k < 4; ++k) r = mix64(r, h[k]);
+  return mix64(r, bytes);
+}
+struct Section {
+  const void* p;
+  size_t bytes;
+};
+size_t pad8(size_t b) { return (b + 7) & ~size_t(7); }
+}  // namespace
+
+// Content key of an edge list: what `edis_graph_save` / `edis_graph_load` files are keyed by.
+extern "C" uint64_t edis_edge_list_key(int64_t n, int64_t n_cols, int64_t e_in, const int64_t* row,
+                                       const int64_t* col, int max_chunk) {
+  uint64_t h = mix64(mix64(mix64(0x45444953ull, n), n_cols), e_in);
+  h = mix64(h, max_chunk <= 0 ? 256 : max_chunk);
+  if (e_in > 0 && row && col) {
+    h = hash_bytes(row, static_cast<size_t>(e_in) * 8, h);
+    h = hash_bytes(col, static_cast<size_t>(e_in) * 8, h);
+  }
+  return h;
+}
+
+extern "C" int edis_graph_save(const edis_graph* g, const char* path, uint64_t key) {
+  EDIS_CHECK_ARG(g && path, "edis_graph_save: null argument");
+  EDIS_CHECK_ARG(g->h_dst_items && g->h_src_items, "edis_graph_save: handle carries no host schedules");
+  // neighbour arrays are stored WITH their heat bits when the handle is device-resident; a
+  // structure-only handle stores plain ids (heat 0) and the loader recomputes nothing
+  std::vector<int32_t> dcol(std::max<int64_t>(g->e, 1)), dcscrow(std::max<int64_t>(g->e, 1));
+  if (g->device >= 0 && g->e > 0) {
+    if (cudaMemcpy(dcol.data(), g->col, g->e * 4, cudaMemcpyDeviceToHost) != cudaSuccess ||
+        cudaMemcpy(dcscrow.data(), g->cscrow, g->e * 4, cudaMemcpyDeviceToHost) != cudaSuccess) {
+      set_error("edis_graph_save: reading the device arrays failed");
+      return EDIS_ERR_CUDA;
+    }
+  } else if (g->e > 0) {
+    memcpy(dcol.data(), g->h_col, g->e * 4);
+    memcpy(dcscrow.data(), g->h_cscrow, g->e * 4);
+  }
+  const Section sec[] = {
+      {g->h_rowptr, static_cast<size_t>(g->n + 1) * 8},        {dcol.data(), static_cast<size_t>(g->e) * 4},
+      {g->h_perm, static_cast<size_t>(g->e_in) * 8},            {g->h_cscptr, static_cast<size_t>(g->n_cols + 1) * 8},
+      {dcscrow.data(), static_cast<size_t>(g->e) * 4},          {g->h_csceid, static_cast<size_t>(g->e) * 4},
+      {g->h_dst_items, static_cast<size_t>(g->dst.n_items) * sizeof(Item)},
+      {g->h_dst_split, static_cast<size_t>(g->dst.n_split) * sizeof(SplitRow)},
+      {g->h_src_items, static_cast<size_t>(g->src.n_items) * sizeof(Item)},
+      {g->h_src_split, static_cast<size_t>(g->src.n_split) * sizeof(SplitRow)}};
+  CacheHeader h = {};
+  h.magic = kCacheMagic; h.version = kCacheVersion; h.max_chunk = static_cast<uint32_t>(g->max_chunk);
+  h.key = key;
+  h.n = g->n; h.n_cols = g->n_cols; h.e = g->e; h.e_in = g->e_in;
+  h.max_in = g->max_in; h.max_out = g->max_out; h.was_sorted = g->was_sorted ? 1 : 0;
+  h.dst_items = g->dst.n_items; h.dst_slots = g->dst.n_slots; h.dst_split = g->dst.n_split;
+  h.src_items = g->src.n_items; h.src_slots = g->src.n_slots; h.src_split = g->src.n_split;
+  uint64_t ph = 0x5eedull;
+  for (const Section& s : sec) {
+    h.payload_bytes += pad8(s.bytes);
+    ph = mix64(ph, hash_bytes(s.p, s.bytes, s.bytes));
+  }
+  h.payload_hash = ph;
+  const std::string tmp = std::string(path) + ".tmp." + std::to_string(static_cast<long long>(getpid()));
+  FILE* f = fopen(tmp.c_str(), "wb");
+  if (!f) {
+    set_error("edis_graph_save: cannot open %s for writing", tmp.c_str());
+    return EDIS_ERR_ARG;
+  }
+  bool ok = fwrite(&h, sizeof(h), 1, f) == 1;
+  const uint64_t zero = 0;
+  for (const Section& s : sec) {
+    if (s.bytes) ok = ok && fwrite(s.p, 1, s.bytes, f) == s.bytes;
+    if (pad8(s.bytes) != s.bytes) ok = ok && fwrite(&zero, 1, pad8(s.bytes) - s.bytes, f) == pad8(s.bytes) - s.bytes;
+  }
+  ok = (fclose(f) == 0) && ok;
+  if (!ok || rename(tmp.c_str(), path) != 0) {       // atomic publish: readers never see a partial file
+    remove(tmp.c_str());
+    set_error("edis_graph_save: writing %s failed", path);
+    return EDIS_ERR_ARG;
+  }
+  return EDIS_OK;
+}
+
+// Returns EDIS_OK and a handle, or EDIS_ERR_STALE (no handle) when the file is missing, truncated,
+// corrupt, of another format version, or was written for another key / chunk size.
+extern "C" int edis_graph_load(const char* path, uint64_t key, int max_chunk, int device, int verify,
+                               edis_graph** out) {
+  EDIS_CHECK_ARG(path && out, "edis_graph_load: null argument");
+  *out = nullptr;
+  if (max_chunk <= 0) max_chunk = 256;
+  const int fd = open(path, O_RDONLY);
+  if (fd < 0) {
+    set_error("edis_graph_load: %s: no such cache file", path);
+    return EDIS_ERR_STALE;
+  }
+  struct stat st;
+  if (fstat(fd, &st) != 0 || static_cast<size_t>(st.st_size) < sizeof(CacheHeader)) {
+    close(fd);
+    set_error("edis_graph_load: %s: truncated", path);
+    return EDIS_ERR_STALE;
+  }
+  const size_t fbytes = static_cast<size_t>(st.st_size);
+  void* map = mmap(nullptr, fbytes, PROT_READ, MAP_PRIVATE, fd, 0);
+  close(fd);
+  if (map == MAP_FAILED) {
+    set_error("edis_graph_load: mmap of %s failed", path);
+    return EDIS_ERR_STALE;
+  }
+  madvise(map, fbytes, MADV_SEQUENTIAL);
+  const CacheHeader h = *static_cast<const CacheHeader*>(map);
+  auto stale = [&](const char* why) {
+    munmap(map, fbytes);
+    set_error("edis_graph_load: %s: %s", path, why);
+    return EDIS_ERR_STALE;
+  };
+  if (h.magic != kCacheMagic || h.version != kCacheVersion) return stale("not an edis graph cache of this version");
+  if (h.key != key) return stale("stale: written for a different input (content key mismatch)");
+  if (static_cast<int>(h.max_chunk) != max_chunk) return stale("stale: written for a different max_chunk");
+  if (h.n <= 0 || h.n_cols < h.n || h.e < 0 || h.e_in < 0) return stale("corrupt header");
+  const size_t sizes[] = {static_cast<size_t>(h.n + 1) * 8, static_cast<size_t>(h.e) * 4,
+                          static_cast<size_t>(h.e_in) * 8,   static_cast<size_t>(h.n_cols + 1) * 8,
+                          static_cast<size_t>(h.e) * 4,      static_cast<size_t>(h.e) * 4,
+                          static_cast<size_t>(h.dst_items) * sizeof(Item), static_cast<size_t>(h.dst_split) * sizeof(SplitRow),
+                          static_cast<size_t>(h.src_items) * sizeof(Item), static_cast<size_t>(h.src_split) * sizeof(SplitRow)};
+  size_t total = 0;
+  for (size_t b : sizes) total += pad8(b);
+  if (total != h.payload_bytes || sizeof(CacheHeader) + total != fbytes) return stale("truncated or corrupt (size mismatch)");
+  const uint8_t* base = static_cast<const uint8_t*>(map) + sizeof(CacheHeader);
+  const uint8_t* secp[10];
+  {
+    const uint8_t* q = base;
+    for (int k = 0; k < 10; ++k) {
+      secp[k] = q;
+      q += pad8(sizes[k]);
+    }
+  }
+  if (verify) {
+    uint64_t ph = 0x5eedull;
+    for (int k = 0; k < 10; ++k) ph = mix64(ph, hash_bytes(secp[k], sizes[k], sizes[k]));
+    if (ph != h.payload_hash) return stale("corrupt (payload checksum mismatch)");
+  }
+  edis_graph* g = new edis_graph();
+  g->n = h.n; g->n_cols = h.n_cols; g->e = h.e; g->e_in = h.e_in;
+  g->max_in = h.max_in; g->max_out = h.max_out; g->was_sorted = h.was_sorted != 0;
+  g->device = device;
+  g->max_chunk = max_chunk;
+  g->dst.n_items = h.dst_items; g->dst.n_slots = h.dst_slots; g->dst.n_split = h.dst_split;
+  g->src.n_items = h.src_items; g->src.n_slots = h.src_slots; g->src.n_split = h.src_split;
+  const int64_t e1 = std::max<int64_t>(h.e, 1);
+  g->h_rowptr = new int64_t[h.n + 1];
+  g->h_col = new int32_t[e1];
+  g->h_perm = new int64_t[std::max<int64_t>(h.e_in, 1)];
+  g->h_cscptr = new int64_t[h.n_cols + 1];
+  g->h_cscrow = new int32_t[e1];
+  g->h_csceid = new int32_t[e1];
+  g->h_dst_items = new Item[std::max<int64_t>(h.dst_items, 1)];
+  g->h_dst_split = new SplitRow[std::max<int64_t>(h.dst_split, 1)];
+  g->h_src_items = new Item[std::max<int64_t>(h.src_items, 1)];
+  g->h_src_split = new SplitRow[std::max<int64_t>(h.src_split, 1)];
+  memcpy(g->h_rowptr, secp[0], sizes[0]);
+  memcpy(g->h_perm, secp[2], sizes[2]);
+  memcpy(g->h_cscptr, secp[3], sizes[3]);
+  memcpy(g->h_csceid, secp[5], sizes[5]);
+  memcpy(g->h_dst_items, secp[6], sizes[6]);
+  memcpy(g->h_dst_split, secp[7], sizes[7]);
+  memcpy(g->h_src_items, secp[8], sizes[8]);
+  memcpy(g->h_src_split, secp[9], sizes[9]);
+  const int32_t* dcol = reinterpret_cast<const int32_t*>(secp[1]);
+  const int32_t* dcscrow = reinterpret_cast<const int32_t*>(secp[4]);
+  for (int64_t k = 0; k < h.e; ++k) {
+    g->h_col[k] = dcol[k] & kIdMask;
+    g->h_cscrow[k] = dcscrow[k] & kIdMask;
+  }
+  int rc = EDIS_OK;
+  if (device >= 0) {
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    if (cudaSetDevice(device) != cudaSuccess) {
+      set_error("edis_graph_load: cudaSetDevice(%d) failed (no CUDA device? there is no CPU fallback)", device);
+      rc = EDIS_ERR_CUDA;
+    } else {
+      cudaDeviceGetAttribute(&g->sm_count, cudaDevAttrMultiProcessorCount, device);
+      // straight from the mapped pages: no intermediate host buffer
+      if (rc == EDIS_OK) rc = upload(&g->rowptr, reinterpret_cast<const int64_t*>(secp[0]), h.n + 1);
+      if (rc == EDIS_OK) rc = upload(&g->col, dcol, h.e);
+      if (rc == EDIS_OK) rc = upload(&g->cscptr, reinterpret_cast<const int64_t*>(secp[3]), h.n_cols + 1);
+      if (rc == EDIS_OK) rc = upload(&g->cscrow, dcscrow, h.e);
+      if (rc == EDIS_OK) rc = upload(&g->csceid, reinterpret_cast<const int32_t*>(secp[5]), h.e);
+      if (rc == EDIS_OK) rc = upload(&g->dst.items, reinterpret_cast<const Item*>(secp[6]), h.dst_items);
+      if (rc == EDIS_OK) rc = upload(&g->dst.split, reinterpret_cast<const SplitRow*>(secp[7]), h.dst_split);
+      if (rc == EDIS_OK) rc = upload(&g->src.items, reinterpret_cast<const Item*>(secp[8]), h.src_items);
+      if (rc == EDIS_OK) rc = upload(&g->src.split, reinterpret_cast<const SplitRow*>(secp[9]), h.src_split);
+      cudaSetDevice(prev_dev);
+    }
+  }
+  munmap(map, fbytes);
+  if (rc != EDIS_OK) {
+    edis_graph_destroy(g);
+    return rc;
+  }
+  *out = g;
   return EDIS_OK;
 }
 

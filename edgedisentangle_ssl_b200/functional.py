@@ -112,6 +112,12 @@ class _timed:
         return False
 
 
+def phase(name):
+    """Time a host-orchestrated phase (GEMMs, exposed collective waits) with CUDA events on the current
+    stream when bench.py has switched the timer on; counts no launches and carries no byte model."""
+    return _timed("phase:" + name, None, 0, None)
+
+
 def _desc(att, C, D, training=False, p=0.0, seed=0):
     return LayerDesc(att=att, C=C, D=D, Dv=D, training=1 if (training and p > 0) else 0, p=float(p),
                      seed=int(seed) & 0xFFFFFFFFFFFFFFFF)
@@ -135,6 +141,48 @@ def _workspace(graph, width, like):
     return torch.empty(nbytes, dtype=torch.uint8, device=like.device), nbytes
 
 
+def disga_forward_raw(graph, d, P, ldp, Q, ldq, V, ldv, a, bias, device, want_sign):
+    """One edis_disga_fwd launch on raw operands (ctypes pointers + row strides).  Allocates and
+    returns (out, hpre, edge_e, stats, esign).  Shared by DisGAFused and parallel.PartitionedLayer."""
+    C, D = d.C, d.D
+    CD = C * D
+    n, e = graph.n, graph.e
+    out = torch.empty(n, CD, dtype=torch.float32, device=device)
+    hpre = torch.empty_like(out)
+    edge_e = torch.empty(e, C, dtype=torch.float32, device=device)
+    stats = torch.empty(n, 2 * C, dtype=torch.float32, device=device)
+    ws, nbytes = _workspace(graph, CD + 2 * C, out)
+    esign = _sign_rec(graph, d, device, want_sign)
+    with _timed("disga_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0),
+                kernel_bytes("fwd", n, graph.n_cols, e, d.att, C, D)):
+        check(lib.edis_disga_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), V, ldv, _ptr(bias),
+                                 _ptr(out), _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(ws), nbytes,
+                                 _stream()), "edis_disga_fwd")
+    return out, hpre, edge_e, stats, esign
+
+
+def disga_backward_raw(graph, d, P, ldp, Q, ldq, V, ldv, a, bias, hpre, edge_e, stats, esign, g_out, g_edge_e,
+                       gP, ldgp, gQ, ldgq, ga, gV, ldgv, device):
+    """edis_disga_bwd_dst + edis_disga_bwd_src on raw operands; the caller owns gP / gQ / gV / ga.
+    Returns gh[n, C*D] (gradient wrt the pre-ELU aggregate; its column sum is the bias gradient)."""
+    C, D, att = d.C, d.D, d.att
+    CD = C * D
+    n, e, nc = graph.n, graph.e, graph.n_cols
+    edge_rec = _edge_rec(graph, d, device)
+    gh = torch.empty(n, CD, dtype=torch.float32, device=device)
+    ws, nbytes = _workspace(graph, 2 * CD + 2 * C, gh)
+    args = (graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), V, ldv, _ptr(bias),
+            _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_out), _ptr(g_edge_e), gP, ldgp, gQ, ldgq,
+            _ptr(ga), gV, ldgv, _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream())
+    with _timed("disga_bwd_dst", graph, 1 + (1 if graph.info["dst_slots"] else 0),
+                kernel_bytes("bwd_dst", n, nc, e, att, C, D)):
+        check(lib.edis_disga_bwd_dst(*args), "edis_disga_bwd_dst")
+    with _timed("disga_bwd_src", graph, 1 + (2 if graph.info["src_slots"] else 0),
+                kernel_bytes("bwd_src", n, nc, e, att, C, D)):
+        check(lib.edis_disga_bwd_src(*args), "edis_disga_bwd_src")
+    return gh
+
+
 class DisGAFused(torch.autograd.Function):
     """All C channels of one DisGALayer: scoring -> sigmoid -> segment softmax -> dropout ->
     aggregation -> (+bias) -> ELU.  Replaces layers.py:349-416 + 500/509 per channel.
@@ -151,7 +199,6 @@ class DisGAFused(torch.autograd.Function):
     @staticmethod
     def forward(ctx, graph, att, C, D, proj, off_p, off_q, off_v, sdst, ssrc, a, bias, training, p, seed):
         proj, ld = _rows(proj, "proj")
-        CD = C * D
         if att == 1:
             sdst, ssrc = sdst.contiguous(), ssrc.contiguous()
             P, Q, ldp, ldq = _ptr(sdst), _ptr(ssrc), C, C
@@ -159,21 +206,11 @@ class DisGAFused(torch.autograd.Function):
             P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
         a = a.contiguous() if a is not None else None
         bias = bias.contiguous() if bias is not None else None
-        n, e = graph.n, graph.e
         if proj.shape[0] != graph.n_cols:
             raise _lib.EdisError("projection has %d rows, graph has %d source nodes" % (proj.shape[0], graph.n_cols))
-        out = torch.empty(n, CD, dtype=torch.float32, device=proj.device)
-        hpre = torch.empty_like(out)
-        edge_e = torch.empty(e, C, dtype=torch.float32, device=proj.device)
-        stats = torch.empty(n, 2 * C, dtype=torch.float32, device=proj.device)
-        ws, nbytes = _workspace(graph, CD + 2 * C, proj)
         d = _desc(att, C, D, training, p, seed)
-        esign = _sign_rec(graph, d, proj.device, any(ctx.needs_input_grad))
-        with _timed("disga_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0),
-                    kernel_bytes("fwd", n, graph.n_cols, e, att, C, D)):
-            check(lib.edis_disga_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a),
-                                     _off(proj, off_v), ld, _ptr(bias), _ptr(out), _ptr(hpre), _ptr(edge_e),
-                                     _ptr(stats), _ptr(esign), _ptr(ws), nbytes, _stream()), "edis_disga_fwd")
+        out, hpre, edge_e, stats, esign = disga_forward_raw(graph, d, P, ldp, Q, ldq, _off(proj, off_v), ld, a, bias,
+                                                            proj.device, any(ctx.needs_input_grad))
         ctx.graph, ctx.d, ctx.offs = graph, d, (off_p, off_q, off_v)
         ctx.has_a, ctx.has_bias = a is not None, bias is not None
         ctx.save_for_backward(proj, sdst, ssrc, a, bias, hpre, edge_e, stats, esign)
@@ -215,18 +252,8 @@ class DisGAFused(torch.autograd.Function):
             else:
                 gQ, ldgq = _off(g_proj, off_q), W
         ga = torch.zeros(C, D, dtype=torch.float32, device=dev) if att == 3 else None
-        edge_rec = _edge_rec(graph, d, dev)
-        gh = torch.empty(n, CD, dtype=torch.float32, device=dev)
-        ws, nbytes = _workspace(graph, 2 * CD + 2 * C, proj)
-        args = (graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _off(proj, off_v), ld, _ptr(bias),
-                _ptr(hpre), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_out), _ptr(g_edge_e), gP, ldgp, gQ, ldgq,
-                _ptr(ga), _off(g_proj, off_v), W, _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream())
-        with _timed("disga_bwd_dst", graph, 1 + (1 if graph.info["dst_slots"] else 0),
-                    kernel_bytes("bwd_dst", n, nc, e, att, C, D)):
-            check(lib.edis_disga_bwd_dst(*args), "edis_disga_bwd_dst")
-        with _timed("disga_bwd_src", graph, 1 + (2 if graph.info["src_slots"] else 0),
-                    kernel_bytes("bwd_src", n, nc, e, att, C, D)):
-            check(lib.edis_disga_bwd_src(*args), "edis_disga_bwd_src")
+        gh = disga_backward_raw(graph, d, P, ldp, Q, ldq, _off(proj, off_v), ld, a, bias, hpre, edge_e, stats, esign,
+                                g_out, g_edge_e, gP, ldgp, gQ, ldgq, ga, _off(g_proj, off_v), W, dev)
         if gq_sep is not None:
             g_proj[:, off_p:off_p + CD] += gq_sep
         gbias = gh.sum(0) if ctx.has_bias else None

@@ -5,6 +5,7 @@ Replaces the reference's dense / COO handling: `data_load.load_data` (data_load.
 layers.py:344.
 """
 import ctypes
+import os
 from ctypes import c_double, c_float, c_int32, c_int64, c_void_p
 
 import numpy as np
@@ -58,6 +59,10 @@ class Graph:
                                          np_ptr(row, c_int64), np_ptr(col, c_int64), int(max_chunk),
                                          self.device.index, ctypes.byref(h)), "edis_graph_create_rect")
         self._h = h
+        self.max_chunk = int(max_chunk)
+        self._read_info()
+
+    def _read_info(self):
         info = np.zeros(10, dtype=np.int64)
         check(lib.edis_graph_info(self._h, np_ptr(info, c_int64)), "edis_graph_info")
         self.n, self.e, self.n_cols = int(info[0]), int(info[1]), int(info[9])
@@ -75,6 +80,58 @@ class Graph:
     @property
     def handle(self):
         return self._h
+
+    # ------------------------------------------------------------------ on-disk cache
+    @staticmethod
+    def content_key(n, row, col, max_chunk=0, n_cols=None):
+        """64-bit content key of an input edge list: what a cache file of this graph is keyed by."""
+        row = np.ascontiguousarray(row, dtype=np.int64)
+        col = np.ascontiguousarray(col, dtype=np.int64)
+        return int(lib.edis_edge_list_key(n, n if n_cols is None else int(n_cols), row.shape[0], np_ptr(row, c_int64),
+                                          np_ptr(col, c_int64), int(max_chunk)))
+
+    def save(self, path, key):
+        """Write rowptr / col / perm / CSC / schedules to `path` (atomic), keyed by `key` (any 64-bit
+        integer naming the INPUT: `Graph.content_key(...)` of the edge list, or a hash of generator
+        parameters) and by this graph's max_chunk."""
+        os.makedirs(os.path.dirname(os.path.abspath(path)) or ".", exist_ok=True)
+        check(lib.edis_graph_save(self._h, os.fsencode(path), int(key) & (2 ** 64 - 1)), "edis_graph_save")
+        return path
+
+    @classmethod
+    def load(cls, path, key, device=None, max_chunk=0, verify=True):
+        """Graph from a cache file written by `save` for the same key and max_chunk, memory-mapped and
+        uploaded to `device`; None when there is no usable file (missing, truncated, corrupt, other
+        format version, other key = stale): the caller rebuilds and saves."""
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        device = torch.device(device)
+        if device.type != "cuda":
+            raise _lib.EdisError("edgedisentangle_ssl_b200 runs on CUDA devices only (got %s); "
+                                 "there is no CPU fallback" % device)
+        dev = torch.device("cuda", device.index if device.index is not None else torch.cuda.current_device())
+        h = c_void_p()
+        rc = lib.edis_graph_load(os.fsencode(path), int(key) & (2 ** 64 - 1), int(max_chunk), dev.index,
+                                 1 if verify else 0, ctypes.byref(h))
+        if rc == _lib.ERR_STALE:
+            return None
+        check(rc, "edis_graph_load")
+        g = cls.__new__(cls)
+        g.device, g._h, g.max_chunk, g._indices = dev, h, int(max_chunk), None
+        g._read_info()
+        g._e_in = int(lib.edis_graph_input_entries(h))
+        return g
+
+    @classmethod
+    def cached(cls, path, n, row, col, device=None, max_chunk=0, n_cols=None):
+        """`Graph(n, row, col, ...)` through a cache file at `path`, keyed by the content of (row, col)."""
+        key = cls.content_key(n, row, col, max_chunk, n_cols)
+        g = cls.load(path, key, device, max_chunk) if path else None
+        if g is None:
+            g = cls(n, row, col, device=device, max_chunk=max_chunk, n_cols=n_cols)
+            if path:
+                g.save(path, key)
+        return g
 
     def workspace_bytes(self, width):
         return int(check(lib.edis_graph_workspace_bytes(self._h, int(width)), "edis_graph_workspace_bytes"))

@@ -7,11 +7,17 @@ One process per GPU (`torch.distributed`, NCCL over NVLink; gloo on CPU for the 
   * the sources its edges read are its own nodes plus a HALO of remote nodes; columns are
     re-indexed compactly (own first, halo after) and the slice becomes a rectangular edis graph;
   * per layer the layer INPUT rows (F or D floats per node, not the 2*C*D projected ones) of the
-    halo nodes are fetched from their owners (point-to-point, volume = halo size); projections
-    are recomputed locally for own + halo rows;
-  * backward returns the halo rows' input gradients to their owners (reverse exchange) and
-    all-reduces the weight gradients.
+    halo nodes reach the rank by ONE collective (`SourceExchange`): a padded all-gather when the halo
+    is most of the graph (a power-law graph cut into ranges: 71 % of all nodes are sources of every
+    rank at 8 ranks), a variable all-to-all of only the needed rows when it is not (locality-ordered
+    graphs); the reverse collective (reduce-scatter / all-to-all) returns input gradients to owners;
+  * projections are recomputed locally: the destination operand P for the rank's OWN rows only, the
+    source operands Q | V for own + halo rows (`PartitionedLayer`, one autograd node per layer with a
+    hand-ordered backward so that the exchange runs under the own-row GEMMs);
+  * weight gradients are all-reduced in one rank-invariant flat bucket.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -23,9 +29,17 @@ def row_ranges(rowptr, world, balance="edges"):
     n = len(rowptr) - 1
     if balance == "nodes":
         return np.linspace(0, n, world + 1).round().astype(np.int64)
+    if n < world:
+        raise ValueError("cannot cut %d rows into %d non-empty ranges" % (n, world))
     target = rowptr[-1] * np.arange(1, world) / world
-    cuts = np.searchsorted(rowptr, target, side="left")
-    return np.concatenate([[0], np.clip(cuts, 0, n), [n]]).astype(np.int64)
+    cuts = np.clip(np.searchsorted(rowptr, target, side="left"), 0, n)
+    b = np.concatenate([[0], cuts, [n]]).astype(np.int64)
+    # a hub row heavier than E/world would leave a neighbour range empty: every rank keeps >= 1 row
+    for r in range(1, world):
+        b[r] = max(b[r], b[r - 1] + 1)
+    for r in range(world - 1, 0, -1):
+        b[r] = min(b[r], b[r + 1] - 1)
+    return b
 
 
 def compact_columns(lo, hi, rows_global, cols_global):
@@ -40,7 +54,7 @@ def compact_columns(lo, hi, rows_global, cols_global):
 
 
 class Partition:
-    """One rank's slice: compact local indexing + the halo exchange plan."""
+    """One rank's slice: compact local indexing + the exchange plans."""
 
     def __init__(self, rank, world, bounds, rows_global, cols_global):
         """rows_global/cols_global: COO (row-major sorted) of the edges whose destination this rank
@@ -52,8 +66,13 @@ class Partition:
         self.n_total = int(bounds[-1])
         self.row_local, self.col_local, self.halo_ids = compact_columns(self.lo, self.hi, rows_global, cols_global)
         self.n_src = self.n_local + len(self.halo_ids)
-        # ---- exchange plan: who owns my halo nodes, and which of my nodes others need
+        # ---- all-gather plan: ranges are padded to the largest one; source row s of this rank sits at
+        # row pad_index[s] of the gathered [world * max_rows, F] buffer
+        self.max_rows = int(np.diff(self.bounds).max())
         owner = np.searchsorted(self.bounds, self.halo_ids, side="right") - 1
+        self.pad_index = np.concatenate([rank * self.max_rows + np.arange(self.n_local, dtype=np.int64),
+                                         owner * self.max_rows + (self.halo_ids - self.bounds[owner])])
+        # ---- all-to-all plan: who owns my halo nodes, and which of my nodes others need
         self.recv_counts = np.bincount(owner, minlength=world).astype(np.int64)   # halo sorted => grouped
         want = [self.halo_ids[owner == r] for r in range(world)]
         if world > 1:
@@ -65,8 +84,20 @@ class Partition:
         self.send_counts = np.array([len(a) for a in asked], dtype=np.int64)
         self.send_idx = (np.concatenate(asked) - self.lo).astype(np.int64) if sum(self.send_counts) else \
             np.zeros(0, dtype=np.int64)
+        # exchange mode: all-gather moves n_total rows per rank, the all-to-all only the halo (but needs a
+        # gather of the rows to send and an index_add on the way back): all-gather once the halo is
+        # more than half of the other ranks' nodes.  All ranks must agree -> decided on the global sum.
+        mode = os.environ.get("EDIS_EXCHANGE", "auto")
+        if mode == "auto":
+            tot = np.array([len(self.halo_ids), self.n_total - self.n_local], dtype=np.int64)
+            if world > 1:
+                g = [None] * world
+                dist.all_gather_object(g, tot.tolist())
+                tot = np.sum(np.array(g, dtype=np.int64), axis=0)
+            mode = "allgather" if 2 * tot[0] > tot[1] else "alltoall"
+        self.mode = mode
         self.graph = None          # set by attach_graph
-        self._send_idx_dev = None
+        self._dev = {}
 
     def attach_graph(self, device, max_chunk=0):
         from .graph import Graph
@@ -74,69 +105,256 @@ class Partition:
                            n_cols=self.n_src)
         return self
 
+    def _on(self, name, arr, device):
+        key = (name, str(device))
+        if key not in self._dev:
+            self._dev[key] = torch.from_numpy(np.ascontiguousarray(arr)).to(device)
+        return self._dev[key]
+
     def send_index(self, device):
-        if self._send_idx_dev is None or self._send_idx_dev.device != device:
-            self._send_idx_dev = torch.from_numpy(self.send_idx).to(device)
-        return self._send_idx_dev
+        return self._on("send", self.send_idx, device)
+
+    def pad_index_dev(self, device):
+        return self._on("pad", self.pad_index, device)
+
+    def halo_pad_index_dev(self, device):
+        return self._on("halo_pad", self.pad_index[self.n_local:], device)
 
 
-def _exchange(send, send_counts, recv_counts, width):
-    """Variable all-to-all of row blocks with point-to-point ops (works on NCCL and gloo)."""
-    world, rank = dist.get_world_size(), dist.get_rank()
-    recv = send.new_empty(int(recv_counts.sum()), width)
-    s_off = np.concatenate([[0], np.cumsum(send_counts)])
-    r_off = np.concatenate([[0], np.cumsum(recv_counts)])
-    ops = []
-    for peer in range(world):
-        if peer == rank:
-            continue
-        if recv_counts[peer]:
-            ops.append(dist.P2POp(dist.irecv, recv[r_off[peer]:r_off[peer + 1]], peer))
-        if send_counts[peer]:
-            ops.append(dist.P2POp(dist.isend, send[s_off[peer]:s_off[peer + 1]], peer))
-    if ops:
-        for w in dist.batch_isend_irecv(ops):
-            w.wait()
-    return recv
+def partition_of_global_graph(idx, n, rank, world, device=None, max_chunk=0, balance="edges"):
+    """This rank's Partition of ONE global graph (strong scaling): `idx` [2, E] is the processed,
+    row-major sorted adjacency every rank holds (or generates from the same seed); destination rows are
+    cut into `world` contiguous ranges balanced by in-edge count.  Collective."""
+    deg = np.bincount(idx[0], minlength=n)
+    rowptr = np.concatenate([[0], np.cumsum(deg)]).astype(np.int64)
+    bounds = row_ranges(rowptr, world, balance)
+    lo, hi = int(bounds[rank]), int(bounds[rank + 1])
+    e0, e1 = int(rowptr[lo]), int(rowptr[hi])
+    part = Partition(rank, world, bounds, idx[0][e0:e1], idx[1][e0:e1])
+    return part.attach_graph(device, max_chunk) if device is not None else part
 
 
-class HaloExchange(torch.autograd.Function):
-    """x_local[n_local, F] -> x_needed[n_local + n_halo, F] (own rows first, then halo rows in
-    ascending global id).  Backward routes the halo rows' gradients back to their owners."""
+# ------------------------------------------------------------------------------- collectives
+class _Pending:
+    """A collective in flight (async_op=True: it runs on the backend's own stream; `wait` makes the
+    CURRENT stream wait for it, the host does not block) plus what turns its buffer into the result."""
+
+    def __init__(self, work, finish):
+        self.work, self.finish = work, finish
+
+    def wait(self):
+        if self.work is not None:
+            self.work.wait()
+        return self.finish()
+
+
+def start_source_gather(x_local, part):
+    """Start fetching the source rows this rank's edges read: -> _Pending whose wait() returns
+    x_src[n_src, F] = own rows followed by the halo rows (ascending global id)."""
+    if part.world == 1:
+        return _Pending(None, lambda: x_local)
+    F_ = x_local.shape[1]
+    dev = x_local.device
+    if part.mode == "allgather":
+        if part.n_local == part.max_rows:
+            pad = x_local.contiguous()
+        else:
+            pad = x_local.new_zeros(part.max_rows, F_)
+            pad[:part.n_local] = x_local
+        buf = x_local.new_empty(part.world * part.max_rows, F_)
+        work = dist.all_gather_into_tensor(buf, pad, async_op=True)
+
+        def finish():
+            halo = buf.index_select(0, part.halo_pad_index_dev(dev))
+            return torch.cat([x_local, halo], 0)
+        return _Pending(work, finish)
+    send = x_local.index_select(0, part.send_index(dev))
+    recv = x_local.new_empty(int(part.recv_counts.sum()), F_)
+    work = dist.all_to_all_single(recv, send, part.recv_counts.tolist(), part.send_counts.tolist(), async_op=True)
+    return _Pending(work, lambda: torch.cat([x_local, recv], 0))
+
+
+def start_source_scatter(g_src, part):
+    """Reverse of start_source_gather for gradients: g_src[n_src, F] (partial gradient of every source
+    row this rank read) -> _Pending whose wait() returns the part of g_local[n_local, F] that comes
+    from OTHER ranks' reads plus this rank's own rows of g_src (sum over ranks of the rows it owns)."""
+    if part.world == 1:
+        return _Pending(None, lambda: g_src)
+    F_ = g_src.shape[1]
+    dev = g_src.device
+    if part.mode == "allgather":
+        buf = g_src.new_zeros(part.world * part.max_rows, F_)
+        buf.index_copy_(0, part.pad_index_dev(dev), g_src)
+        out = g_src.new_empty(part.max_rows, F_)
+        work = dist.reduce_scatter_tensor(out, buf, async_op=True)
+        return _Pending(work, lambda: out[:part.n_local])
+    send = g_src[part.n_local:].contiguous()
+    back = g_src.new_empty(int(part.send_counts.sum()), F_)
+    work = dist.all_to_all_single(back, send, part.send_counts.tolist(), part.recv_counts.tolist(), async_op=True)
+
+    def finish():
+        g_local = g_src[:part.n_local].clone()
+        g_local.index_add_(0, part.send_index(dev), back)
+        return g_local
+    return _Pending(work, finish)
+
+
+class SourceExchange(torch.autograd.Function):
+    """x_local[n_local, F] -> x_src[n_local + n_halo, F] (own rows first, then halo rows in
+    ascending global id).  Backward routes the source rows' gradients back to their owners."""
 
     @staticmethod
     def forward(ctx, x_local, part):
+        from .functional import phase
         ctx.part = part
-        if part.world == 1:
-            return x_local
-        send = x_local.index_select(0, part.send_index(x_local.device)).contiguous()
-        recv = _exchange(send, part.send_counts, part.recv_counts, x_local.shape[1])
-        return torch.cat([x_local, recv], 0)
+        with phase("exchange_exposed"):
+            return start_source_gather(x_local, part).wait()
 
     @staticmethod
     def backward(ctx, g):
-        part = ctx.part
-        if part.world == 1:
-            return g, None
-        g_local = g[:part.n_local].clone()
-        back = _exchange(g[part.n_local:].contiguous(), part.recv_counts, part.send_counts, g.shape[1])
-        g_local.index_add_(0, part.send_index(g.device), back)
-        return g_local, None
+        from .functional import phase
+        with phase("exchange_exposed"):
+            return start_source_scatter(g.contiguous(), ctx.part).wait(), None
 
 
-def get_em_partitioned(enc, fusers, x_local, part, layer_fn=None):
-    """`DISGAT.get_em` (models.py:217-252) over a destination-range partition: returns this
-    rank's rows of [feature_1, feature_2]."""
-    if layer_fn is None:
+HaloExchange = SourceExchange      # round-1 name
+
+
+# ------------------------------------------------------------------------------- one layer
+def _edis_kernels():
+    """(forward, backward) of the fused layer on raw operands: libedis through functional.py."""
+    from . import functional as Fn
+
+    def fwd(graph, d, P, QV, a, bias, want_sign):
+        CD = d.C * d.D
+        return Fn.disga_forward_raw(graph, d, Fn._ptr(P), P.stride(0), Fn._ptr(QV), QV.stride(0),
+                                    Fn._off(QV, CD), QV.stride(0), a, bias, P.device, want_sign)
+
+    def bwd(graph, d, P, QV, a, bias, saved, g_out, g_edge_e):
+        CD = d.C * d.D
+        hpre, edge_e, stats, esign = saved
+        gP = torch.empty_like(P)
+        gQV = torch.empty_like(QV)
+        ga = torch.zeros(d.C, d.D, dtype=torch.float32, device=P.device) if d.att == 3 else None
+        gh = Fn.disga_backward_raw(graph, d, Fn._ptr(P), P.stride(0), Fn._ptr(QV), QV.stride(0), Fn._off(QV, CD),
+                                   QV.stride(0), a, bias, hpre, edge_e, stats, esign, g_out, g_edge_e,
+                                   Fn._ptr(gP), gP.stride(0), Fn._ptr(gQV), gQV.stride(0), ga, Fn._off(gQV, CD),
+                                   gQV.stride(0), P.device)
+        return gP, gQV, ga, (gh.sum(0) if bias is not None else None)
+
+    return fwd, bwd
+
+
+def _project(x, w):
+    """Node projection at fp32 accuracy: 3xTF32 on the tensor cores for big node counts (see
+    functional.Proj3xTF32), plain fp32 otherwise (and always on CPU)."""
+    if x.is_cuda and x.shape[0] >= 4096 and os.environ.get("EDIS_PROJ3X", "1") != "0":
+        from .functional import _mm_3xtf32
+        return _mm_3xtf32(x, w)
+    return x @ w
+
+
+class PartitionedLayer(torch.autograd.Function):
+    """One DISGAT layer (gnn_type AT / GCN, att 3) on a destination-range partition, as ONE autograd node:
+
+      forward   start the source exchange of x_local -> P = x_local W_top (own rows only, runs under the
+                exchange) -> x_src = own + halo rows -> Q|V = x_src [W_bot | W_val] -> fused kernel
+      backward  fused backward kernels -> gP[n_local], gQ|gV[n_src] -> (layer 2 only) input gradient of
+                the source rows, sent back to the owners by the reverse collective, which runs under the
+                weight-gradient GEMMs and the own-row part -> sum.
+
+    Layer 1 never needs an input gradient (x = features), which removes the largest of the per-rank
+    GEMMs over own + halo rows.  Saved for the backward: x_src (F floats per source row), P, Q|V, and the
+    kernel's own records.  `kernels` = (fwd, bwd) callables on raw operands (libedis by default; the CPU
+    gloo tests plug in the oracle)."""
+
+    @staticmethod
+    def forward(ctx, x_local, w_top, w_qv, a, bias, part, desc, kernels):
+        from .functional import phase
+        pend = start_source_gather(x_local, part)
+        with phase("gemm_fwd"):
+            P = _project(x_local, w_top)                   # overlaps with the exchange
+        with phase("exchange_exposed"):
+            x_src = pend.wait()
+        with phase("gemm_fwd"):
+            QV = _project(x_src, w_qv)
+        kfwd, _ = kernels
+        a_c = a.contiguous()
+        bias_c = bias.contiguous() if bias is not None else None
+        out, hpre, edge_e, stats, esign = kfwd(part.graph, desc, P, QV, a_c, bias_c, True)
+        ctx.part, ctx.desc, ctx.kernels = part, desc, kernels
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x_local, x_src, w_top, w_qv, a_c, bias_c, P, QV, hpre, edge_e, stats, esign)
+        ctx.set_materialize_grads(False)
+        return out, edge_e
+
+    @staticmethod
+    def backward(ctx, g_out, g_edge_e):
+        from .functional import _xt_g
+        x_local, x_src, w_top, w_qv, a, bias, P, QV, hpre, edge_e, stats, esign = ctx.saved_tensors
+        part, d = ctx.part, ctx.desc
+        if g_out is None:
+            g_out = torch.zeros(part.n_local, d.C * d.D, dtype=torch.float32, device=P.device)
+        g_out = g_out.contiguous()
+        if g_edge_e is not None:
+            g_edge_e = g_edge_e.contiguous()
+        gP, gQV, ga, gbias = ctx.kernels[1](part.graph, d, P, QV, a, bias, (hpre, edge_e, stats, esign), g_out,
+                                            g_edge_e)
+        del P, QV, hpre, edge_e, stats, esign
+        from .functional import phase
+        need_gx = ctx.needs_input_grad[0]
+        pend = None
+        with phase("gemm_bwd"):
+            if need_gx:
+                pend = start_source_scatter(gQV @ w_qv.t(), part)     # [n_src, F] -> owners (async)
+            g_wqv = _xt_g(x_src, gQV) if ctx.needs_input_grad[2] else None      # these run under the collective
+            g_wtop = _xt_g(x_local, gP) if ctx.needs_input_grad[1] else None
+            gx_own = gP @ w_top.t() if need_gx else None
+        gx = None
+        if need_gx:
+            with phase("exchange_exposed"):
+                gx = pend.wait()
+            gx = gx + gx_own
+        return gx, g_wtop, g_wqv, (ga if ctx.needs_input_grad[3] else None), gbias, None, None, None
+
+
+def layer_partitioned(chs, x_local, part, training=None, kernels=None):
+    """C DisGALayer channels on this rank's rows: -> out[n_local, C*D] (= cat_c elu(h'_c)), edge_e."""
+    from . import _lib
+    from .layers import _next_seed
+    l0 = chs[0]
+    C, D, Fin, att, gnn = len(chs), l0.out_features, l0.in_features, l0.att_type, l0.gnn_type
+    if att != 3 or gnn not in ("AT", "GCN"):
+        # generic route: exchange the inputs, then the single-GPU layer on own + halo rows
         from .layers import run_channels
+        out, edge_e, _ = run_channels(chs, SourceExchange.apply(x_local, part), part.graph)
+        return out, edge_e
+    w_top = torch.cat([l.W[:Fin] for l in chs], 1)
+    w_qv = torch.cat([l.W[Fin:] for l in chs] + [(l.W_em if gnn == "AT" else l.ag_layer.weight) for l in chs], 1)
+    a = torch.cat([l.a.reshape(1, D) for l in chs], 0)
+    bias = None
+    if gnn == "GCN" and l0.ag_layer.bias is not None:
+        bias = torch.cat([l.ag_layer.bias for l in chs], 0)
+    training = l0.training if training is None else training
+    p = l0.dropout
+    # the rank is folded into the seed: ranks hash LOCAL edge ids and must not draw identical masks
+    seed = (_next_seed() + 0x632BE59BD9B4E019 * (part.rank + 1)) & (2 ** 64 - 1) if (training and p > 0) else 0
+    desc = _lib.LayerDesc(att=att, C=C, D=D, Dv=D, training=1 if (training and p > 0) else 0, p=float(p), seed=seed)
+    return PartitionedLayer.apply(x_local, w_top, w_qv, a, bias, part, desc, kernels or _edis_kernels())
 
-        def layer_fn(chs, x_need, graph):
-            return run_channels(chs, x_need, graph)[0]
+
+def get_em_partitioned(enc, fusers, x_local, part, layer_fn=None, kernels=None):
+    """`DISGAT.get_em` (models.py:217-252) over a destination-range partition: returns this
+    rank's rows of [feature_1, feature_2].  layer_fn(chs, x_src, graph) -> out replaces the whole layer
+    after a plain SourceExchange (round-1 test hook); kernels = (fwd, bwd) replaces only the fused
+    kernels inside PartitionedLayer."""
     x = F.dropout(x_local, enc.dropout, training=enc.training)
     feats = []
     for layer, chs in enumerate((enc.attentions1, enc.attentions2)):
-        x_need = HaloExchange.apply(x, part)
-        out = layer_fn(chs, x_need, part.graph)
+        if layer_fn is not None:
+            out = layer_fn(chs, SourceExchange.apply(x, part), part.graph)
+        else:
+            out = layer_partitioned(chs, x, part, kernels=kernels)[0]
         fused = enc._fuse(layer, fusers, out, x)
         x = F.dropout(fused, enc.dropout, training=enc.training)
         feats.append(x)
@@ -153,33 +371,32 @@ class AllGatherRows(torch.autograd.Function):
         ctx.part = part
         if part.world == 1:
             return x_local
-        sizes = np.diff(part.bounds)
-        m = int(sizes.max())
+        m = part.max_rows
         pad = x_local.new_zeros(m, x_local.shape[1])
         pad[:part.n_local] = x_local
-        bufs = [torch.empty_like(pad) for _ in range(part.world)]
-        dist.all_gather(bufs, pad)
-        return torch.cat([b[:int(s)] for b, s in zip(bufs, sizes)], 0)
+        buf = x_local.new_empty(part.world * m, x_local.shape[1])
+        dist.all_gather_into_tensor(buf, pad)
+        sizes = np.diff(part.bounds)
+        if int(sizes.min()) == m:
+            return buf
+        return torch.cat([buf[r * m:r * m + int(sizes[r])] for r in range(part.world)], 0)
 
     @staticmethod
     def backward(ctx, g_all):
         part = ctx.part
         if part.world == 1:
             return g_all, None
-        if dist.get_backend() == "nccl":
-            sizes = np.diff(part.bounds)
-            m = int(sizes.max())
-            chunks = []
+        m = part.max_rows
+        sizes = np.diff(part.bounds)
+        if int(sizes.min()) == m:
+            buf = g_all.contiguous()
+        else:
+            buf = g_all.new_zeros(part.world * m, g_all.shape[1])
             for r in range(part.world):
-                c = g_all.new_zeros(m, g_all.shape[1])
-                c[:int(sizes[r])] = g_all[int(part.bounds[r]):int(part.bounds[r + 1])]
-                chunks.append(c)
-            out = torch.empty_like(chunks[0])
-            dist.reduce_scatter(out, chunks)
-            return out[:part.n_local].contiguous(), None
-        g = g_all.contiguous().clone()            # gloo has no reduce_scatter: all-reduce, keep own rows
-        dist.all_reduce(g)
-        return g[part.lo:part.hi].contiguous(), None
+                buf[r * m:r * m + int(sizes[r])] = g_all[int(part.bounds[r]):int(part.bounds[r + 1])]
+        out = g_all.new_empty(m, g_all.shape[1])
+        dist.reduce_scatter_tensor(out, buf)
+        return out[:part.n_local].contiguous(), None
 
 
 def ssl_pair_loss_partitioned(enc, fusers, x_local, part, pairs, labels, ranges, n_pos_total, m_total,
@@ -238,19 +455,35 @@ def sample_pairs_partitioned(part, pos_key_local, generator=None):
     return pairs, lab, int(cnt[0].item()), int(cnt[1].item())
 
 
-def allreduce_grads(params):
-    """Sum the weight gradients over ranks (one flat bucket; the per-rank losses add up)."""
+def allreduce_grads(params, async_op=False):
+    """Sum the weight gradients over ranks in ONE flat bucket (the per-rank losses add up).  The bucket
+    covers every parameter -- a missing gradient (a rank whose slice never touched the parameter) is sent
+    as zeros -- so its size is the same on all ranks whatever each rank's autograd graph looked like.
+    async_op=True returns a callable that waits and writes the sums back (overlap with later work)."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
-        return
-    grads = [p.grad for p in params if p.grad is not None]
-    if not grads:
-        return
-    flat = torch.cat([g.reshape(-1) for g in grads])
-    dist.all_reduce(flat)
-    off = 0
-    for g in grads:
-        g.copy_(flat[off:off + g.numel()].view_as(g))
-        off += g.numel()
+        return (lambda: None) if async_op else None
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return (lambda: None) if async_op else None
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1) for p in params])
+    seen = torch.tensor([0.0 if p.grad is None else 1.0 for p in params], device=flat.device)
+    flat = torch.cat([flat, seen])
+    work = dist.all_reduce(flat, async_op=True)
+
+    def finish():
+        work.wait()
+        off = 0
+        got = flat[-len(params):].tolist() if any(p.grad is None for p in params) else None
+        for i, p in enumerate(params):
+            k = p.numel()
+            if p.grad is not None:
+                p.grad.copy_(flat[off:off + k].view_as(p))
+            elif got is not None and got[i] > 0:          # some other rank produced a gradient for it
+                p.grad = flat[off:off + k].view_as(p).clone()
+            off += k
+    if async_op:
+        return finish
+    finish()
 
 
 # --------------------------------------------------------------------------- synthetic workload

@@ -31,6 +31,7 @@ extern "C" {
 #define EDIS_ERR_CUDA (-2)
 #define EDIS_ERR_UNSUPPORTED (-3)
 #define EDIS_ERR_WORKSPACE (-4)
+#define EDIS_ERR_STALE (-5) /* edis_graph_load: cache file missing, corrupt, or written for other input */
 
 const char* edis_last_error(void);
 /* library / build identification: "edis <ver> sm_100a" */
@@ -76,6 +77,8 @@ void edis_graph_destroy(edis_graph* g);
  * [6]=max in-degree, [7]=max out-degree, [8]=1 if the input was already sorted (perm = identity),
  * [9]=n_cols */
 int edis_graph_info(const edis_graph* g, int64_t info[10]);
+/* number of entries of the INPUT edge list the handle was built from (= length of `perm`) */
+int64_t edis_graph_input_entries(const edis_graph* g);
 /* copies of the structure arrays to HOST buffers (any may be NULL): rowptr[n+1], col[e],
  * perm[e_in] (input entry k -> CSR slot perm[k]; sized by the INPUT entry count, duplicates
  * map to the same slot), cscptr[n_cols+1], cscrow[e], csceid[e] */
@@ -83,6 +86,24 @@ int edis_graph_export(const edis_graph* g, int64_t* rowptr, int32_t* col, int64_
                       int64_t* cscptr, int32_t* cscrow, int32_t* csceid);
 /* bytes of scratch the layer ops need for a node tensor of `width` floats per row */
 int64_t edis_graph_workspace_bytes(const edis_graph* g, int64_t width);
+
+/* On-disk graph cache.  Replaces the per-start dense detour of data_load.py:39-77 /
+ * utils.py:163-170 (39.5 s on cora_full) and, by construction, the stale-cache hazard of
+ * pretrainer.py:390-398 (`./resource/<ds>/DisEdges.pt`, keyed by dataset name only): a file is
+ * keyed by a 64-bit content key chosen by the caller and by max_chunk, and is rejected otherwise.
+ *   edis_edge_list_key  content key of an input edge list (+ sizes and max_chunk): the key to use
+ *                       when the cache stands for `edis_graph_create_rect` on exactly this input
+ *   edis_graph_save     writes rowptr / col / perm / CSC / both schedules (+ heat bits) to `path`
+ *                       atomically (temp file + rename)
+ *   edis_graph_load     memory-maps `path`, checks magic / version / key / max_chunk / sizes (and the
+ *                       payload checksum when verify != 0), uploads straight from the mapping to
+ *                       `device` (-1: structure-only handle).  EDIS_ERR_STALE = no usable file (not
+ *                       an error of the caller: rebuild and save). */
+uint64_t edis_edge_list_key(int64_t n, int64_t n_cols, int64_t e_in, const int64_t* row,
+                            const int64_t* col, int max_chunk);
+int edis_graph_save(const edis_graph* g, const char* path, uint64_t key);
+int edis_graph_load(const char* path, uint64_t key, int max_chunk, int device, int verify,
+                    edis_graph** out);
 
 /* ------------------------------------------------------------------ fused DisGALayer
  * One call computes ALL C channels of one DISGAT layer.  Replaces, per channel,

@@ -194,3 +194,83 @@ def test_adjacency_builder_edge_cases():
     got = np.zeros((4, 4))
     got[idx[0], idx[1]] = val
     assert np.allclose(got, dense, atol=1e-7) and np.count_nonzero(got) == idx.shape[1]
+
+
+# ------------------------------------------------------------------ on-disk cache
+def _load_host(path, key, max_chunk=0, verify=1):
+    h = ctypes.c_void_p()
+    rc = lib.edis_graph_load(os.fsencode(path), key, max_chunk, -1, verify, ctypes.byref(h))
+    return rc, h
+
+
+def _export(h, n, nc, e, e_in):
+    rowptr, col, perm = np.empty(n + 1, np.int64), np.empty(max(e, 1), np.int32), np.empty(max(e_in, 1), np.int64)
+    cscptr, cscrow, csceid = np.empty(nc + 1, np.int64), np.empty(max(e, 1), np.int32), np.empty(max(e, 1), np.int32)
+    check(lib.edis_graph_export(h, np_ptr(rowptr, ctypes.c_int64), np_ptr(col, ctypes.c_int32),
+                                np_ptr(perm, ctypes.c_int64), np_ptr(cscptr, ctypes.c_int64),
+                                np_ptr(cscrow, ctypes.c_int32), np_ptr(csceid, ctypes.c_int32)), "edis_graph_export")
+    return rowptr, col[:e], perm[:e_in], cscptr, cscrow[:e], csceid[:e]
+
+
+@pytest.mark.parametrize("shuffle,max_chunk", [(False, 0), (True, 16)])
+def test_cache_round_trip_is_identical(tmp_path, shuffle, max_chunk):
+    """edis_graph_save -> edis_graph_load (memory-mapped) reproduces every array, the schedules' sizes
+    and the input -> slot permutation, for sorted and unsorted (+ duplicate) inputs and split rows."""
+    rng = np.random.RandomState(5)
+    n = 400
+    idx, _ = og.build_adjacency(n, np.concatenate([rng.randint(0, n, 3000), np.zeros(300, np.int64)]),
+                                np.concatenate([rng.randint(0, n, 3000), rng.randint(0, n, 300)]))
+    row, col = idx[0], idx[1]
+    if shuffle:
+        o = rng.permutation(len(row))
+        row, col = np.concatenate([row[o], row[:50]]), np.concatenate([col[o], col[:50]])    # unsorted + duplicates
+    g = HostGraph(n, row, col, max_chunk=max_chunk)
+    key = int(lib.edis_edge_list_key(n, n, len(row), np_ptr(np.ascontiguousarray(row), ctypes.c_int64),
+                                     np_ptr(np.ascontiguousarray(col), ctypes.c_int64), max_chunk))
+    path = str(tmp_path / "g.edisg")
+    check(lib.edis_graph_save(g.h, os.fsencode(path), key), "edis_graph_save")
+    rc, h = _load_host(path, key, max_chunk)
+    assert rc == 0
+    try:
+        info = (ctypes.c_int64 * 10)()
+        check(lib.edis_graph_info(h, info), "edis_graph_info")
+        keys = ("n", "e", "dst_items", "dst_slots", "src_items", "src_slots", "max_in", "max_out", "was_sorted", "n_cols")
+        assert dict(zip(keys, [int(v) for v in info])) == g.info
+        assert int(lib.edis_graph_input_entries(h)) == len(row)
+        got = _export(h, n, n, g.info["e"], len(row))
+        for a, b in zip(got, (g.rowptr, g.col, g.perm, g.cscptr, g.cscrow, g.csceid)):
+            assert np.array_equal(a, b)
+        if max_chunk:
+            assert g.info["dst_slots"] > 0            # the hub row 0 was split: schedules with slots round-trip
+    finally:
+        lib.edis_graph_destroy(h)
+
+
+def test_cache_rejects_stale_and_damaged_files(tmp_path):
+    """A cache written for other input (key), another chunk size, a truncated or bit-flipped file, or a
+    missing one is EDIS_ERR_STALE -- never silently used (the hazard of pretrainer.py:390-398)."""
+    rng = np.random.RandomState(6)
+    n = 120
+    idx, _ = og.build_adjacency(n, rng.randint(0, n, 700), rng.randint(0, n, 700))
+    g = HostGraph(n, idx[0], idx[1])
+    key = int(lib.edis_edge_list_key(n, n, idx.shape[1], np_ptr(np.ascontiguousarray(idx[0]), ctypes.c_int64),
+                                     np_ptr(np.ascontiguousarray(idx[1]), ctypes.c_int64), 0))
+    other = idx.copy()
+    other[1, 5] = (other[1, 5] + 1) % n                 # one changed edge -> another key
+    key2 = int(lib.edis_edge_list_key(n, n, idx.shape[1], np_ptr(np.ascontiguousarray(other[0]), ctypes.c_int64),
+                                      np_ptr(np.ascontiguousarray(other[1]), ctypes.c_int64), 0))
+    assert key != key2
+    path = str(tmp_path / "g.edisg")
+    check(lib.edis_graph_save(g.h, os.fsencode(path), key), "edis_graph_save")
+    assert _load_host(path, key)[0] == 0
+    assert _load_host(path, key2)[0] == _lib.ERR_STALE and "stale" in _lib.last_error()
+    assert _load_host(path, key, max_chunk=64)[0] == _lib.ERR_STALE
+    assert _load_host(str(tmp_path / "missing.edisg"), key)[0] == _lib.ERR_STALE
+    blob = open(path, "rb").read()
+    open(str(tmp_path / "cut.edisg"), "wb").write(blob[: len(blob) // 2])
+    assert _load_host(str(tmp_path / "cut.edisg"), key)[0] == _lib.ERR_STALE
+    flipped = bytearray(blob)
+    flipped[len(blob) - 40] ^= 0x10
+    open(str(tmp_path / "flip.edisg"), "wb").write(bytes(flipped))
+    assert _load_host(str(tmp_path / "flip.edisg"), key)[0] == _lib.ERR_STALE and "checksum" in _lib.last_error()
+    assert _load_host(str(tmp_path / "flip.edisg"), key, verify=0)[0] == 0       # checksum is opt-out

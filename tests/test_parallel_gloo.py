@@ -24,13 +24,13 @@ def free_port():
     return p
 
 
-def make_problem():
+def make_problem(gnn="AT"):
     import edgedisentangle_ssl_b200 as edis
     from edgedisentangle_ssl_b200.utils import get_parser
     rng = np.random.RandomState(3)
     n, fin = 90, 12
     idx, _ = og.build_adjacency(n, rng.randint(0, n, 500), rng.randint(0, n, 500))
-    args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--att=3", "--gnn_type=AT", "--nhead=2",
+    args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--att=3", "--gnn_type=" + gnn, "--nhead=2",
                                     "--nhid=8", "--dropout=0.0"])
     torch.manual_seed(0)
     enc = edis.DISGAT(args, nfeat=fin, nhid=8, nclass=8, nheads=2, dropout=0.0)
@@ -116,6 +116,101 @@ def enc_get_em_oracle(enc, fus, x, idx, n):
         return oracle_layer(chs, x_need, part.row_local, part.col_local, part.n_local)
 
     return par.get_em_partitioned(enc, fus, x, part, layer_fn)
+
+
+def oracle_kernels(part):
+    """(fwd, bwd) on raw operands for parallel.PartitionedLayer, computed by plain torch on the CPU
+    (layers.py:375-379, 392-399 on P_i + Q_j): stands in for libedis in the gloo tests."""
+    row = torch.from_numpy(part.row_local)
+    col = torch.from_numpy(part.col_local)
+
+    def forward(P, QV, a, bias, C, D):
+        CD = C * D
+        z = P[row] + QV[col, :CD]
+        e = (torch.nn.functional.leaky_relu(z, 0.01).reshape(-1, C, D) * a.reshape(1, C, D)).sum(-1)       # [E, C]
+        w = torch.exp(torch.sigmoid(e))
+        den = torch.zeros(part.n_local, C).index_add_(0, row, w)
+        alpha = w / den[row]
+        msg = alpha.unsqueeze(-1) * QV[col, CD:].reshape(-1, C, D)
+        agg = torch.zeros(part.n_local, C, D).index_add_(0, row, msg).reshape(-1, CD)
+        if bias is not None:
+            agg = agg + bias
+        return torch.nn.functional.elu(agg), e
+
+    def fwd(graph, d, P, QV, a, bias, want_sign):
+        with torch.no_grad():
+            out, e = forward(P, QV, a, bias, d.C, d.D)
+        return out, None, e, None, None
+
+    def bwd(graph, d, P, QV, a, bias, saved, g_out, g_edge_e):
+        leaves = [t.detach().requires_grad_(True) for t in (P, QV, a)]
+        b = bias.detach().requires_grad_(True) if bias is not None else None
+        with torch.enable_grad():
+            out, e = forward(leaves[0], leaves[1], leaves[2], b, d.C, d.D)
+            tot = (out * g_out).sum() + (0 if g_edge_e is None else (e * g_edge_e).sum())
+        gs = torch.autograd.grad(tot, leaves + ([b] if b is not None else []))
+        return gs[0], gs[1], gs[2], (gs[3] if b is not None else None)
+
+    return fwd, bwd
+
+
+def layer_worker(rank, world, port, out_q, mode, gnn):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EDIS_EXCHANGE=mode)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from edgedisentangle_ssl_b200 import parallel as par
+        n, idx, args, enc, fus, x, R = make_problem(gnn)
+        part = par.partition_of_global_graph(idx, n, rank, world)
+        assert part.mode == mode
+        x_loc = x[part.lo:part.hi].clone().requires_grad_(True)
+        feats = par.get_em_partitioned(enc, fus, x_loc, part, kernels=oracle_kernels(part))
+        (feats[-1] * R[part.lo:part.hi]).sum().backward()
+        params = [p for m in [enc] + fus for p in m.parameters()]
+        par.allreduce_grads(params)
+        out_q.put((rank, {"feat": feats[-1].detach().numpy().copy(), "lo": part.lo, "hi": part.hi,
+                          "gx": x_loc.grad.numpy().copy(),
+                          "grads": {k: v.grad.numpy().copy() for k, v in enc.named_parameters() if v.grad is not None}}))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,gnn,world", [("allgather", "AT", 2), ("alltoall", "AT", 2), ("allgather", "GCN", 3)])
+def test_partitioned_layer_node_matches_single_process(mode, gnn, world):
+    """parallel.PartitionedLayer (own-row P, own+halo Q|V, overlapped exchange, hand-ordered backward)
+    through both exchange collectives: features, INPUT gradient and weight gradients equal the
+    single-process run of the same oracle kernels."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=layer_worker, args=(r, world, port, q, mode, gnn)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    from edgedisentangle_ssl_b200 import parallel as par
+    n, idx, args, enc, fus, x, R = make_problem(gnn)
+    part = par.Partition(0, 1, np.array([0, n]), idx[0], idx[1])
+    xg = x.clone().requires_grad_(True)
+    feats = par.get_em_partitioned(enc, fus, xg, part, kernels=oracle_kernels(part))
+    (feats[-1] * R).sum().backward()
+    for r in range(world):
+        got = results[r]
+        assert torch.allclose(torch.from_numpy(got["feat"]), feats[-1][got["lo"]:got["hi"]].detach(), rtol=1e-5, atol=1e-6)
+        assert torch.allclose(torch.from_numpy(got["gx"]), xg.grad[got["lo"]:got["hi"]], rtol=2e-4, atol=1e-6)
+        for k, v in enc.named_parameters():
+            if v.grad is not None:
+                assert torch.allclose(torch.from_numpy(got["grads"][k]), v.grad, rtol=2e-4, atol=1e-6), k
+
+
+def test_row_ranges_never_empty_with_a_dominant_hub():
+    from edgedisentangle_ssl_b200 import parallel as par
+    deg = np.array([1, 1, 1000, 1, 1, 1, 1, 1])
+    rowptr = np.concatenate([[0], np.cumsum(deg)])
+    for world in (2, 4, 8):
+        b = par.row_ranges(rowptr, world)
+        assert b[0] == 0 and b[-1] == 8 and np.all(np.diff(b) >= 1), b
 
 
 def test_row_ranges_and_compact_indexing():
