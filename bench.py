@@ -2,20 +2,25 @@
 """bench.py -- DISGAT fwd+bwd edges/s on B200 (the BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl edis|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = DISGAT.get_em forward + backward of a scalar loss, 2 layers x C channels, train
-mode (dropout on), on the synthetic power-law graph of BASELINE config[3] (2.4M nodes, ~62M
+mode (dropout on), on the synthetic power-law graph of BASELINE config[3] (2.4M nodes, ~63M
 edges, F=100, C=8, D=64, att=3, gnn_type=AT).  Prints ONE JSON line (rank 0).
   value      edges/s with inputs resident in HBM (CUDA events, max over ranks)
   e2e        same through the public API with the features coming from pinned HOST memory
              every step (H2D inside the timed region) and the loss read back (D2H)
   roofline   the dominant kernel's algorithmic bytes / CUDA-event time vs the measured HBM peak
-  cpu_baseline  the CPU oracle port of the reference's path on a bounded sample of the workload
-`--impl reference` times that CPU port as the reference arm (no GPU work).
-Multi-GPU (torchrun, N > 1): destination-range partition of the graph, one rank per GPU, features
-all-gathered per layer and weight gradients all-reduced over NCCL (see DESIGN.md section e).
+  breakdown  ms per step: sparse kernels / projection GEMMs / exposed exchange / the rest
+  cpu_baseline  the UNMODIFIED reference (oracle/_ref) on a bounded sample of the workload, host cores
+N > 1 (one rank per GPU, NCCL): by default STRONG scaling -- the SAME 63M-edge graph, destination rows
+range-partitioned over the ranks (BASELINE config[3] "at 1/2/4/8 B200 with dst-partitioned CSR");
+`--scaling weak` is the round-1 community workload (one 2.4M-node community per rank, a stated
+`locality` fraction of edges inside it).  `--config B` = BASELINE config[4] (10M nodes / 500M edges).
+`--impl reference` times the reference's own CPU path (rank 0 only, no GPU work, no libedis).
 """
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -36,21 +41,31 @@ def parse():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="edis", choices=["edis", "reference"])
-    ap.add_argument("--nodes", type=int, default=2_400_000)
-    ap.add_argument("--raw-edges", type=int, default=30_600_000, help="directed draws before symmetrise/dedup")
-    ap.add_argument("--feat", type=int, default=100)
+    ap.add_argument("--config", default="A", choices=["A", "B"], help="A = BASELINE config[3], B = config[4]")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--locality", type=float, default=0.9, help="weak scaling: fraction of edge draws inside a rank")
+    ap.add_argument("--nodes", type=int, default=None)
+    ap.add_argument("--raw-edges", type=int, default=None, help="directed draws before symmetrise/dedup")
+    ap.add_argument("--feat", type=int, default=None)
     ap.add_argument("--nhead", type=int, default=8)
     ap.add_argument("--nhid", type=int, default=64)
     ap.add_argument("--att", type=int, default=3)
     ap.add_argument("--gnn_type", default="AT")
     ap.add_argument("--dropout", type=float, default=0.1)
-    ap.add_argument("--cpu-nodes", type=int, default=12_000, help="CPU-baseline sample: nodes")
-    ap.add_argument("--cpu-raw-edges", type=int, default=150_000, help="CPU-baseline sample: raw edge draws")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-budget-s", type=float, default=12.0, help="cpu_baseline leg: seconds per reference step")
+    ap.add_argument("--ref-total-s", type=float, default=200.0, help="--impl reference: budget of the whole run")
     ap.add_argument("--max-chunk", type=int, default=0)
     ap.add_argument("--no-epoch-metric", action="store_true", help="skip the cora_full epoch-ms secondary metric")
-    ap.add_argument("--graph-cache", default=None, help="npy file caching the generated graph (tuning sweeps)")
-    return ap.parse_args()
+    ap.add_argument("--no-ssl-metric", action="store_true", help="skip the SupEdge step secondary metric")
+    ap.add_argument("--cache-dir", default=os.environ.get("EDIS_CACHE_DIR", os.path.join(ROOT, ".cache")),
+                    help="graph cache directory ('' = no cache)")
+    a = ap.parse_args()
+    base = {"A": (2_400_000, 30_600_000, 100), "B": (10_000_000, 246_000_000, 64)}[a.config]
+    a.nodes = a.nodes or base[0]
+    a.raw_edges = a.raw_edges or base[1]
+    a.feat = a.feat or base[2]
+    return a
 
 
 def model_args(a):
@@ -61,40 +76,42 @@ def model_args(a):
     return args
 
 
+def workload_config(a, world, e_full=None, extra=None):
+    name = {"A": "ogbn-products shape (BASELINE config[3])", "B": "10M nodes / 500M edges (BASELINE config[4])"}[a.config]
+    if world > 1 and a.scaling == "weak":
+        shape = ("WEAK scaling: %d communities of N=%d nodes / %d raw draws each (one per rank), locality=%.2f of the "
+                 "draws inside the rank's community" % (world, a.nodes, a.raw_edges, a.locality))
+    else:
+        shape = "ONE graph N=%d, raw draws=%d%s" % (
+            a.nodes, a.raw_edges, "" if world == 1 else ", destination rows range-partitioned over %d ranks (strong "
+            "scaling, no planted locality)" % world)
+    cfg = {"workload": "synthetic power-law graph, %s: %s, F=%d, C=%d, D=%d, att=%d, gnn_type=%s, full-batch "
+                       "DISGAT.get_em fwd+bwd, train mode dropout=%g" % (name, shape, a.feat, a.nhead, a.nhid, a.att,
+                                                                         a.gnn_type, a.dropout),
+           "scaling": "n/a (1 GPU)" if world == 1 else a.scaling,
+           "locality": (a.locality if (world > 1 and a.scaling == "weak") else None),
+           "l2_policy": "inputs larger than L2 (node tensors are GBs; no flush needed)"}
+    if e_full is not None:
+        cfg["edges"] = int(e_full)
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
 # ---------------------------------------------------------------------------------- CPU arm
-def cpu_port_rate(a, steps, warmup, threads):
-    """edges/s of the oracle port (oracle/disgat.py: the reference's per-channel eager path)."""
-    from oracle import disgat as od
-    from oracle import graph as og
-    from edgedisentangle_ssl_b200.synthetic import power_law_graph
-    torch.set_num_threads(threads)
-    idx = torch.from_numpy(power_law_graph(a.cpu_nodes, a.cpu_raw_edges, seed=1))
-    n, e = a.cpu_nodes, idx.shape[1]
-    gen = torch.Generator().manual_seed(0)
-    C, D, F = a.nhead, a.nhid, a.feat
-    p = {}
-    for layer, fin in ((1, F), (2, D)):
-        for c in range(C):
-            pre = "attention%d_%d." % (layer, c)
-            p[pre + "W"] = (torch.randn((2 * fin if a.att == 3 else fin), D, generator=gen) * 0.1).requires_grad_(True)
-            p[pre + "a"] = (torch.randn((D if a.att == 3 else 2 * D), 1, generator=gen) * 0.1).requires_grad_(True)
-            p[pre + "W_em"] = (torch.randn(fin, D, generator=gen) * 0.1).requires_grad_(True)
-    fus = [{"fuse.weight": (torch.randn(D, C * D, generator=gen) * 0.05).requires_grad_(True),
-            "fuse.bias": torch.zeros(D, requires_grad=True)} for _ in range(2)]
-    x = torch.randn(n, F, generator=gen)
-    R = torch.randn(n, D, generator=gen)
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        r = od.disgat_traverse(p, fus, x, idx, C, a.att, a.gnn_type, dropout=a.dropout, training=True)
-        loss = (r["feats"][-1] * R).sum()
-        loss.backward()
-        for v in list(p.values()) + [w for f in fus for w in f.values()]:
-            v.grad = None
-        if it >= warmup:
-            times.append(time.perf_counter() - t0)
+def cpu_reference_leg(a, step_budget_s, steps, warmup, threads):
+    """The reference's own CPU path (oracle/_ref, unmodified; the oracle port only if that is absent) on a
+    bounded power-law sample sized for ~`step_budget_s` seconds per step (oracle.ref_arm.sized_workload:
+    E = 2M doubling, BASELINE.md section 4, or smaller when 2M does not fit the budget)."""
+    from oracle import ref_arm
+    wl, _ = ref_arm.sized_workload(a.feat, a.nhead, a.nhid, a.att, a.gnn_type, a.dropout, threads, step_budget_s)
+    for _ in range(max(warmup, 1)):
+        wl.step()
+    times = [wl.step() for _ in range(max(steps, 1))]
     sec = float(np.mean(times))
-    return e / sec, sec, n, e
+    return {"value": wl.e / sec, "unit": "edges/s", "cores": threads, "kind": wl.kind,
+            "sample": "%s, same F/C/D/att/gnn/dropout, %d timed steps of %.1f s (config A/B themselves do not fit the "
+                      "reference: [E, 2F] temporaries and N x N samplers)" % (wl.describe(), len(times), sec)}, sec, wl
 
 
 def run_reference_arm(a):
@@ -102,32 +119,23 @@ def run_reference_arm(a):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    rate, sec, n, e = cpu_port_rate(a, a.steps, a.warmup, threads)
-    sample = "oracle port, power-law sample n=%d E=%d (F=%d C=%d D=%d att=%d %s), %d steps" % (
-        n, e, a.feat, a.nhead, a.nhid, a.att, a.gnn_type, a.steps)
+    budget = max(1.0, a.ref_total_s / max(a.steps + max(a.warmup, 1) + 3, 1))
+    cpu, sec, wl = cpu_reference_leg(a, budget, a.steps, a.warmup, threads)
+    world = int(os.environ.get("WORLD_SIZE", str(a.gpus)))
     line = {
-        "impl": "reference", "metric": "DISGAT fwd+bwd edges/s", "value": rate, "unit": "edges/s",
+        "impl": "reference", "metric": "DISGAT fwd+bwd edges/s", "value": cpu["value"], "unit": "edges/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, e_full=None),
-        "cpu_baseline": {"value": rate, "unit": "edges/s", "cores": threads, "kind": "port", "sample": sample},
-        "e2e": {"value": rate, "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "higher_is_better": True, "scaling": "weak" if world == 1 else a.scaling, "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic", "config": workload_config(a, world),
+        "same_config": False,
+        "same_config_note": "same model / F / C / D / att / gnn / dropout and the same graph law; the graph is a bounded "
+                            "sample (E in the line) because the reference cannot hold the full one -- its rate is per "
+                            "edge, so the ratio compares edges/s, not wall time of equal work",
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": "edges/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(a, e_full, extra=None):
-    cfg = {"workload": "synthetic power-law graph, ogbn-products shape (BASELINE config[3]): "
-                       "N=%d, raw draws=%d, F=%d, C=%d, D=%d, att=%d, gnn_type=%s, full-batch DISGAT.get_em fwd+bwd, "
-                       "train mode dropout=%g" % (a.nodes, a.raw_edges, a.feat, a.nhead, a.nhid, a.att, a.gnn_type,
-                                                 a.dropout),
-           "l2_policy": "inputs larger than L2 (node tensors are GBs; no flush needed)"}
-    if e_full is not None:
-        cfg["edges"] = int(e_full)
-    if extra:
-        cfg.update(extra)
-    return cfg
 
 
 # ---------------------------------------------------------------------------------- cora_full epoch
@@ -148,6 +156,7 @@ def cora_full_epoch_ms():
                       ("device_sampler_sklearn", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "1"}),
                       ("device_sampler_device_metrics", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "device"}),
                       ("device_sampler_no_metrics", {"EDIS_SAMPLER": "device", "EDIS_HOST_METRICS": "0"})):
+        env = dict(env, EDIS_SYNTH_FEATURES="1")      # cora_full's feature blob is missing from the snapshot
         old = {k: os.environ.get(k) for k in env}
         os.environ.update(env)
         try:
@@ -196,7 +205,7 @@ def supedge_step(margs, enc, graph, x_dev, steps=2):
         ms = ev0.elapsed_time(ev1) / steps
         return {"ms_per_step": ms, "pairs": m, "pairs_per_s": m / (ms * 1e-3), "edges_per_s": graph.e / (ms * 1e-3),
                 "loss": float(log["loss_heads_sup"]), "steps": steps,
-                "note": "SupEdgeTrainer.train_step on the config-A graph: O(M) device sampler + pair scoring "
+                "note": "SupEdgeTrainer.train_step on the bench graph: O(M) device sampler + pair scoring "
                         "(2 layers x %d channels) + edis_ssl_wmse + backward + Adam" % margs.nhead}
     except Exception as exc:                                       # secondary metric: never lose the headline
         return {"error": "%s: %s" % (type(exc).__name__, exc)}
@@ -205,6 +214,52 @@ def supedge_step(margs, enc, graph, x_dev, steps=2):
             os.environ.pop("EDIS_SAMPLER", None)
         else:
             os.environ["EDIS_SAMPLER"] = old
+
+
+def supedge_step_partitioned(a, enc, fus, part, x_dev, params, steps=2):
+    """The same SupEdge step over the destination-range partition (pretrainer.py:683-763 per rank: pairs
+    sampled in the rank's rows, columns scored against the all-gathered layer input, losses normalised by
+    the GLOBAL counts, gradients all-reduced, Adam)."""
+    import torch.distributed as dist
+    from edgedisentangle_ssl_b200 import parallel as par
+    try:
+        dev = x_dev.device
+        ex = part.graph.export()
+        rows = np.repeat(np.arange(part.n_local, dtype=np.int64), np.diff(ex["rowptr"])) + part.lo
+        src_ids = np.concatenate([np.arange(part.lo, part.hi, dtype=np.int64), part.halo_ids])
+        pos_key = torch.from_numpy(rows * part.n_total + src_ids[ex["col"].astype(np.int64)]).to(dev)
+        pos_key = torch.sort(pos_key)[0]
+        opt = torch.optim.Adam(params, lr=1e-3)
+        gen = torch.Generator(device=dev).manual_seed(7 + part.rank)
+
+        def one():
+            pairs, lab, n_pos, m_tot = par.sample_pairs_partitioned(part, pos_key, gen)
+            loss = par.ssl_pair_loss_partitioned(enc, fus, x_dev, part, [pairs], [lab], [(0, a.nhead)], [n_pos], [m_tot])
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            par.allreduce_grads(params)
+            opt.step()
+            return loss.detach(), m_tot
+        one()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(steps):
+            loss, m_tot = one()
+        ev1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t = torch.tensor([ev0.elapsed_time(ev1) / steps, float(loss)], device=dev, dtype=torch.float64)
+        tm = t.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t)
+        return {"ms_per_step": float(tm[0]), "pairs": int(m_tot), "pairs_per_s": m_tot / (float(tm[0]) * 1e-3),
+                "loss": float(t[1]), "steps": steps,
+                "note": "SupEdge step over the partition: per-rank O(M) sampler, pair scoring vs the all-gathered "
+                        "layer input, edis_ssl_wmse with global counts, backward, grad all-reduce, Adam; max over ranks"}
+    except Exception as exc:
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
 
 
 # ---------------------------------------------------------------------------------- clocks
@@ -252,45 +307,92 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-# ---------------------------------------------------------------------------------- GPU arm
+# ---------------------------------------------------------------------------------- workload
+def _gen_key(a):
+    """64-bit key of the generator's parameters: names a cached graph without generating it."""
+    s = "power_law_graph v1 n=%d m=%d seed=0 max_chunk=%d" % (a.nodes, a.raw_edges, a.max_chunk)
+    return int.from_bytes(hashlib.blake2b(s.encode(), digest_size=8).digest(), "little")
+
+
+def global_graph_indices(a, rank, world, barrier):
+    """[2, E] processed adjacency of the ONE bench graph, generated once per box (rank 0) and shared
+    with the other ranks / later runs through the cache directory as a memory-mapped .npy."""
+    from edgedisentangle_ssl_b200.synthetic import power_law_graph
+    path = os.path.join(a.cache_dir, "coo_%016x.npy" % _gen_key(a)) if a.cache_dir else None
+    if path and os.path.exists(path):
+        return np.load(path, mmap_mode="r"), True
+    idx = None
+    if rank == 0 or not path:
+        idx = power_law_graph(a.nodes, a.raw_edges, seed=0)
+        if path:
+            os.makedirs(a.cache_dir, exist_ok=True)
+            tmp = path + ".tmp%d.npy" % os.getpid()
+            np.save(tmp, idx)
+            os.replace(tmp, path)
+    if world > 1 and path:
+        barrier()
+        if idx is None:
+            idx = np.load(path, mmap_mode="r")
+    return idx, False
+
+
 def main():
     a = parse()
     if a.impl == "reference":
         return run_reference_arm(a)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if a.gpus > 1 and world == 1:
+        # launched without torchrun: start one rank per GPU ourselves
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(a.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29511"] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
 
     import torch.distributed as dist
     import edgedisentangle_ssl_b200 as edis
     from edgedisentangle_ssl_b200 import functional as Fn
-    from edgedisentangle_ssl_b200.synthetic import power_law_graph
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the edis arm has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    par = part = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
         from edgedisentangle_ssl_b200 import parallel as par
 
-    # ---- workload (weak scaling: every rank owns a graph of the same size) -------------------
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- workload ---------------------------------------------------------------------------
     t0 = time.time()
+    cache_hit = False
+    strong = world == 1 or a.scaling == "strong"
     if world == 1:
-        if a.graph_cache and os.path.exists(a.graph_cache):
-            idx = np.load(a.graph_cache)
-        else:
-            idx = power_law_graph(a.nodes, a.raw_edges, seed=0)
-            if a.graph_cache:
-                np.save(a.graph_cache, idx)
-        graph = edis.Graph(a.nodes, idx[0], idx[1], device=dev, max_chunk=a.max_chunk)
-        n_local, n_total, e_local = a.nodes, a.nodes, graph.e
+        gpath = os.path.join(a.cache_dir, "graph_%016x.edisg" % _gen_key(a)) if a.cache_dir else None
+        graph = edis.Graph.load(gpath, _gen_key(a), dev, a.max_chunk) if gpath else None
+        cache_hit = graph is not None
+        if graph is None:
+            idx, _ = global_graph_indices(a, 0, 1, barrier)
+            graph = edis.Graph(a.nodes, idx[0], idx[1], device=dev, max_chunk=a.max_chunk)
+            if gpath:
+                graph.save(gpath, _gen_key(a))
+            del idx
+        n_local, n_total, e_local, lo = a.nodes, a.nodes, graph.e, 0
+    elif strong:
+        n_total = a.nodes
+        idx, cache_hit = global_graph_indices(a, rank, world, barrier)
+        part = par.partition_of_global_graph(idx, n_total, rank, world, device=dev, max_chunk=a.max_chunk)
         del idx
+        graph, n_local, e_local, lo = part.graph, part.n_local, part.graph.e, part.lo
     else:
         n_total = a.nodes * world
         part = par.build_partitioned_power_law(n_total, a.raw_edges * world, seed=0, rank=rank, world=world,
-                                                device=dev, max_chunk=a.max_chunk)
-        graph, n_local, e_local = part.graph, part.n_local, part.graph.e
+                                                device=dev, locality=a.locality, max_chunk=a.max_chunk)
+        graph, n_local, e_local, lo = part.graph, part.n_local, part.graph.e, part.lo
     setup_s = time.time() - t0
 
     margs = model_args(a)
@@ -299,9 +401,25 @@ def main():
     fus = [edis.FuseLayer(margs, a.nhead, nfeat=a.nhid).to(dev), edis.FuseLayer(margs, a.nhead, nfeat=a.nhid).to(dev)]
     enc.train()
     params = [p for m in [enc] + fus for p in m.parameters()]
-    gen = torch.Generator().manual_seed(1234 + rank)
-    x_host = torch.randn(n_local, a.feat, generator=gen).pin_memory()
+    # features / loss weights: rows [lo, lo + n_local) of one global seeded stream per 64K-row block, so the
+    # strong-scaling runs at every N work on the SAME node features
+    def rows_of(width, seed):
+        blk = 65536
+        out = torch.empty(n_local, width)
+        b0 = lo // blk
+        pos = 0
+        while pos < n_local:
+            g = torch.Generator().manual_seed(seed * 1_000_003 + b0)
+            chunk = torch.randn(blk, width, generator=g)
+            s = (lo + pos) - b0 * blk
+            take = min(blk - s, n_local - pos)
+            out[pos:pos + take] = chunk[s:s + take]
+            pos += take
+            b0 += 1
+        return out
+    x_host = rows_of(a.feat, 1234).pin_memory()
     x_dev = x_host.to(dev)
+    R = rows_of(a.nhid, 99).to(dev)
     # e2e: double-buffered input -- the H2D copy of step k+1 runs on a side stream under step k
     x_bufs = [x_dev, torch.empty_like(x_dev)]
     copy_stream = torch.cuda.Stream(device=dev)
@@ -314,7 +432,6 @@ def main():
             copy_stream.wait_event(consumed[b])
             x_bufs[b].copy_(x_host, non_blocking=True)
             copied[b].record(copy_stream)
-    R = torch.randn(n_local, a.nhid, device=dev)
     loss_host = torch.zeros(1).pin_memory()
 
     def step(from_host):
@@ -331,7 +448,8 @@ def main():
         loss = (feats[-1] * R).sum()
         loss.backward()
         if world > 1:
-            par.allreduce_grads(params)
+            with Fn.phase("grad_allreduce"):
+                par.allreduce_grads(params)
         if from_host:
             loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
             consumed[state["k"] % 2].record(torch.cuda.current_stream())
@@ -339,11 +457,6 @@ def main():
         for p in params:
             p.grad = None
         return loss
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
 
     def timed(from_host, k):
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -395,9 +508,15 @@ def main():
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     # per kernel: SURVEY 8(d) algorithmic bytes and this implementation's own byte model, both
     # recorded per call by functional.kernel_bytes (layer 1 and layer 2 may run different plans)
-    per = {}
+    per, phases = {}, {}
     for k, v in kernel_list.items():
-        if not v or kernel_bytes[k][0] is None:
+        if not v:
+            continue
+        if k.startswith("phase:"):
+            phases[k[6:]] = float(np.sum(v) / a.steps)
+            continue
+        if kernel_bytes[k][0] is None:
+            phases[k] = float(np.sum(v) / a.steps)
             continue
         ms = np.array(v)
         alg_b = sum(m["alg"] for m in kernel_bytes[k])
@@ -408,8 +527,8 @@ def main():
                   "ms_per_step": float(ms.sum() / a.steps)}
     dom = max(per, key=lambda k: per[k]["ms_per_step"]) if per else None
     roof = None
+    tot_ms = sum(v["ms_per_step"] for v in per.values())
     if dom:
-        tot_ms = sum(v["ms_per_step"] for v in per.values())
         tot_alg = sum(v["bytes_per_launch"] * v["launches_per_step"] for v in per.values())
         roof = {"bound": "hbm", "kernel": dom, "achieved": per[dom]["gbs"], "peak": peak, "unit": "GB/s",
                 "frac": per[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
@@ -417,45 +536,67 @@ def main():
                 "moved_frac": per[dom]["moved_gbs"] / peak,
                 "note": "achieved = SURVEY 8(d) gather-model bytes of the reference layer / CUDA-event time; "
                         "moved_* = bytes this implementation must move with no L2 reuse (sign record instead "
-                        "of re-gathered rows, F floats for a shared operand); traffic = ncu DRAM bytes",
+                        "of re-gathered rows, F floats for a shared operand); traffic = ncu DRAM bytes "
+                        "(profiles/traffic.json, config A on one GPU)",
                 "all_sparse_kernels": {"ms_per_step": tot_ms, "gbs": tot_alg / (tot_ms * 1e-3) / 1e9,
                                        "frac": tot_alg / (tot_ms * 1e-3) / 1e9 / peak},
                 "plan": plan, "kernels": per}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath) and world == 1 and a.config == "A":
             roof["traffic"] = json.load(open(tpath)).get(dom)
+    step_ms = ms_res / a.steps
+    breakdown = {"ms_per_step": step_ms, "sparse_kernels_ms": tot_ms,
+                 "projection_gemm_ms": phases.get("gemm_fwd", 0.0) + phases.get("gemm_bwd", 0.0) or None,
+                 "exchange_exposed_ms": phases.get("exchange_exposed"),
+                 "grad_allreduce_ms": phases.get("grad_allreduce"),
+                 "note": "rank 0, CUDA events on the compute stream; projection_gemm = node projections and their "
+                         "backward inside the partitioned layer (N > 1 only: at N = 1 they are ordinary autograd "
+                         "GEMMs and sit in the remainder); exchange_exposed = time the compute stream waits for the "
+                         "source all-gather / reduce-scatter; remainder = fuser GEMMs, dropout, ELU, loss"}
+    known = sum(v for v in (breakdown["sparse_kernels_ms"], breakdown["projection_gemm_ms"],
+                            breakdown["exchange_exposed_ms"], breakdown["grad_allreduce_ms"]) if v)
+    breakdown["remainder_ms"] = step_ms - known
 
+    secondary = None
+    if not a.no_ssl_metric:
+        if world == 1:
+            secondary = {"supedge_step": supedge_step(margs, enc, graph, x_dev)}
+        else:
+            secondary = {"supedge_step": supedge_step_partitioned(a, enc, fus, part, x_dev, params)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
     cpu = None
     if world == 1 and not a.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        rate, sec, cn, ce = cpu_port_rate(a, 2, 1, threads)
-        cpu = {"value": rate, "unit": "edges/s", "cores": threads, "kind": "port",
-               "sample": "oracle port on a power-law sample n=%d E=%d, same F/C/D/att/gnn, 2 steps of %.1f s"
-                         % (cn, ce, sec)}
+        cpu, _, _ = cpu_reference_leg(a, a.cpu_budget_s, 1, 1, os.cpu_count() or 1)
     graph_info = graph.info
-    secondary = None
-    if world == 1 and not a.no_epoch_metric:
-        secondary = {"supedge_step_config_a": supedge_step(margs, enc, graph, x_dev)}
-        del enc, fus, x_dev, R, graph
+    part_info = None
+    if part is not None:
+        part_info = {"rows_rank0": part.n_local, "sources_rank0": part.n_src, "halo_rank0": len(part.halo_ids),
+                     "exchange": part.mode}
+    if world == 1 and not a.no_epoch_metric and a.config == "A":
+        del enc, fus, x_dev, R, graph, x_bufs
         torch.cuda.empty_cache()
-        secondary["cora_full_epoch_ms"] = cora_full_epoch_ms()
+        secondary = secondary or {}
+        try:
+            secondary["cora_full_epoch_ms"] = cora_full_epoch_ms()
+        except Exception as exc:
+            secondary["cora_full_epoch_ms"] = {"error": "%s: %s" % (type(exc).__name__, exc)}
     line = {
         "metric": "DISGAT fwd+bwd edges/s", "value": value, "unit": "edges/s", "n_gpus": world,
-        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_res / a.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(a, e_total, {"nodes_total": n_total, "setup_s": round(setup_s, 1),
-                                               "parallelism": "single GPU" if world == 1 else "dst-range x%d" % world,
-                                               "graph": graph_info}),
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": step_ms, "higher_is_better": True,
+        "scaling": "weak" if world == 1 else a.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(a, world, e_total, {
+            "nodes_total": n_total, "setup_s": round(setup_s, 1), "graph_cache_hit": bool(cache_hit),
+            "parallelism": "single GPU" if world == 1 else "dst-range x%d" % world,
+            "graph": graph_info, "partition": part_info}),
         "e2e": {"value": e2e_value, "unit": "edges/s", "ms_per_step": ms_e2e / a.steps,
-                "h2d_bytes_per_step": int(x_host.numel() * 4), "d2h_bytes_per_step": 4,
-                "note": "every step's features come from pinned host memory (one H2D copy per step, double-buffered: "
-                        "the copy for step k+1 runs on a side stream under step k) and the loss is read back; graph "
-                        "handle resident (built once, like the reference's adj.cuda())"},
-        "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+                "h2d_bytes_per_step": int(n_total * a.feat * 4), "d2h_bytes_per_step": 4 * world,
+                "note": "every step's features come from pinned host memory (one H2D copy per step and rank, "
+                        "double-buffered: the copy for step k+1 runs on a side stream under step k) and the loss is "
+                        "read back; graph handle resident (built once, like the reference's adj.cuda())"},
+        "gpu_launches": launches, "clocks": clk, "roofline": roof, "breakdown": breakdown, "cpu_baseline": cpu,
         "secondary": secondary,
     }
     print(json.dumps(line), flush=True)

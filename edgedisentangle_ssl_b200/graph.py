@@ -162,8 +162,9 @@ class Graph:
 
     # ------------------------------------------------------------------ constructors
     @classmethod
-    def from_sparse(cls, adj, max_chunk=0):
-        """Graph of a torch sparse COO adjacency; cached on the tensor object."""
+    def from_sparse(cls, adj, max_chunk=0, cache_dir=None):
+        """Graph of a torch sparse COO adjacency; cached on the tensor object and, when `cache_dir`
+        (default: $EDIS_CACHE_DIR) is set, on disk keyed by the content of its index list."""
         g = getattr(adj, "_edis_graph", None)
         if g is not None:
             return g
@@ -175,7 +176,13 @@ class Graph:
         if not adj.is_cuda:
             raise _lib.EdisError("adjacency must live on a CUDA device; there is no CPU fallback")
         idx = adj.coalesce().indices().cpu().numpy()
-        g = cls(adj.shape[0], idx[0], idx[1], device=adj.device, max_chunk=max_chunk)
+        cache_dir = cache_dir or os.environ.get("EDIS_CACHE_DIR")
+        if cache_dir:
+            key = cls.content_key(adj.shape[0], idx[0], idx[1], max_chunk)
+            g = cls.cached(os.path.join(cache_dir, "graph_%016x.edisg" % key), adj.shape[0], idx[0], idx[1],
+                           device=adj.device, max_chunk=max_chunk)
+        else:
+            g = cls(adj.shape[0], idx[0], idx[1], device=adj.device, max_chunk=max_chunk)
         try:
             adj._edis_graph = g
         except Exception:  # pragma: no cover

@@ -116,19 +116,22 @@ def run(argv=None, data_root="data", epoch_hook=None, ckpt_root=".", save_every=
         if epoch % 40 == 0:
             for tr in down:
                 log.update(tr.test([features, adj_of(args.used_edge)], labels, epoch))
+            if args.case and down:
+                # case study on disentanglement (main.py:290-302): inside the every-40-epochs block, right
+                # after `test` (so every model is still in eval mode: no dropout in the statistics, and the
+                # CPU / numpy RNG streams are consumed at the reference's positions), for the LAST
+                # downstream trainer like the reference's leftover loop variable.  The scalars are what the
+                # reference sends to tensorboard; its matplotlib heat maps are out of scope, the maps
+                # themselves are returned
+                with torch.no_grad():
+                    dist, at_cor, feat_cor = down[-1].analyze_disentangle(features, adj_of(args.used_edge))
+                log["att_correlation_layer1"], log["att_correlation_layer2"] = dist
+                log["att_correlation_maps"] = [c.cpu() for c in at_cor]
+                log["feat_correlation_maps"] = [c.cpu() for c in feat_cor]
         if args.finetune:
             for step in range(args.steps):
                 for tr in down:
                     log.update(tr.train_step([features, adj_of(args.used_edge)], labels, epoch))
-        if args.case:
-            # case study on disentanglement (main.py:291-352): the scalars the reference sends to
-            # tensorboard; its matplotlib heat maps are out of scope, the maps themselves are returned
-            for tr in down:
-                with torch.no_grad():
-                    dist, at_cor, feat_cor = tr.analyze_disentangle(features, adj_of(args.used_edge))
-                log["att_correlation_layer1"], log["att_correlation_layer2"] = dist
-                log["att_correlation_maps"] = [c.cpu() for c in at_cor]
-                log["feat_correlation_maps"] = [c.cpu() for c in feat_cor]
         for i, tr in enumerate(ssl_trainers):
             log.update(tr.train_step([features, adj_of(args.pre_edge[i])], ssl_labels[i]))
         torch.cuda.synchronize()

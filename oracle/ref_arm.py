@@ -141,23 +141,32 @@ class Workload:
 
 
 def sized_workload(feat, C, D, att, gnn, dropout, threads, budget_s, start_edges=2_000_000, max_edges=64_000_000,
-                   deg=26.3):
-    """start at E = 2 M and double while one step is predicted to fit `budget_s`
-    seconds (and the [E, 2F] temporaries fit host RAM).  Returns (Workload, seconds of its first step)."""
+                   deg=26.3, probe_edges=250_000):
+    """Bounded sample of the bench workload for one CPU step of about `budget_s` seconds.
+
+    BASELINE.md section 4: E = 2 M, doubling while a step is predicted to fit the budget and the
+    [E, 2F] temporaries fit host RAM.  The prediction comes from one timed step on a `probe_edges` graph
+    (the rate per edge is flat in E: the path is a chain of streaming index / scatter ops).  When even
+    2 M edges do not fit the budget (few host cores, or the driver's 20 + 5 steps in a few minutes) the
+    sample shrinks in steps of `probe_edges` instead -- the line states the E it ran.
+    Returns (Workload, seconds of the probe-predicted step)."""
+    probe = Workload(int(probe_edges / deg), int(probe_edges * 0.4853), feat, C, D, att, gnn, dropout, threads)
+    probe.step()                                   # first call: allocator / thread-pool warm-up
+    per_edge = probe.step() / probe.e
+    try:
+        avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
+    except (ValueError, OSError):
+        avail = 8 << 30
+    # att=3 gathers [E, 2F] fp32 per channel and autograd keeps ~3 such temporaries per channel alive
+    e_mem = int(0.5 * avail / ((2 * feat + 3 * D) * 4 * 3 * max(C // 4, 1)))
     e = start_edges
-    wl = sec = None
-    while True:
-        n = int(e / deg)
-        cand = Workload(n, int(e * 0.4853), feat, C, D, att, gnn, dropout, threads)     # raw draws ~ E / 2.06
-        s = cand.step()
-        wl, sec = cand, s
-        # att=3 gathers [E, 2F] fp32 per channel plus autograd saves: ~E * (2F + 3D) * 4 * 3 bytes live
-        nxt = e * 2
-        mem_next = nxt * (2 * feat + 3 * D) * 4 * 3
-        try:
-            avail = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE")
-        except (ValueError, OSError):
-            avail = 8 << 30
-        if s * 2.2 > budget_s or nxt > max_edges or mem_next > 0.5 * avail:
-            return wl, sec
-        e = nxt
+    if per_edge * e > budget_s:
+        e = max(probe_edges, int(budget_s / per_edge / probe_edges) * probe_edges)
+    else:
+        while per_edge * e * 2 <= budget_s and e * 2 <= max_edges:
+            e *= 2
+    e = max(probe_edges, min(e, e_mem))
+    if e == probe.e or abs(e - probe.e) < probe_edges // 2:
+        return probe, per_edge * probe.e
+    del probe
+    return Workload(int(e / deg), int(e * 0.4853), feat, C, D, att, gnn, dropout, threads), per_edge * e

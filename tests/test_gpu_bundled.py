@@ -1,0 +1,198 @@
+"""Numerical parity ON THE BASELINE GRAPHS (bundled cora / cora_full / chameleon), not on toys.
+
+Two layers x C=4 channels of DISGAT, eval mode, forward AND backward, every tensor compared over ALL
+of its entries with the CPU oracle run on the box's host cores (oracle/ is pinned to the reference by
+tests/test_oracle_golden.py), plus the committed samples the UNMODIFIED reference produced on the same
+graphs and weights (tests/golden/bundled_ref.npz, made by tests/golden/make_golden_bundled.py):
+raw logits `edge_e`, alpha, elu(h'), feature_2, the three SSL losses, and -- bit for bit -- the SSL
+pair sets of the reference's samplers.  BASELINE.md gate: <= 1e-5 relative on alpha, aggregated
+features and each SSL loss; chameleon is the hard case (real features with |x| up to ~892, sigmoid
+saturating on 1-4 % of the edges, max in-degree 733).  chameleon runs all nine att x gnn_type
+combinations, cora and cora_full att 3 / AT.  Gradients: 2e-5, or 16x the fp32 oracle's own error
+against its float64 evaluation (cancellation-dominated sums), per tensor.
+"""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import edgedisentangle_ssl_b200 as edis
+from edgedisentangle_ssl_b200 import functional as Fn
+from edgedisentangle_ssl_b200 import sampler
+from oracle import disgat as od
+from helpers import load, rel_err
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+DEV = "cuda:0"
+RT = 1e-5
+SEED, C, D = 11, 4, 64
+COMBOS = [("cora", 3, "AT"), ("cora_full", 3, "AT")] + [("chameleon", a, g) for a in (1, 2, 3)
+                                                         for g in ("AT", "SAGE", "GCN")]
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+_DATA = {}
+
+
+def dataset(ds):
+    if ds not in _DATA:
+        from edgedisentangle_ssl_b200 import data_load
+        from edgedisentangle_ssl_b200.utils import get_parser
+        args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--dataset=" + ds])
+        adj, x, labels = data_load.load_data(args, path=os.path.join(ROOT, "data", ds) + "/", dataset=ds, edge_type=1)
+        _DATA[ds] = (adj.coalesce(), x, labels)
+    return _DATA[ds]
+
+
+def build_edis(att, gnn, fin):
+    """Same torch seed and constructor order as make_golden_bundled.build -> identical weights."""
+    from edgedisentangle_ssl_b200.utils import get_parser
+    args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--att=%d" % att, "--gnn_type=" + gnn,
+                                    "--nhead=%d" % C, "--nhid=%d" % D, "--dropout=0.1"])
+    args.size, args.cuda, args.hetero = fin, True, False
+    torch.manual_seed(SEED)
+    enc = edis.DISGAT(args, nfeat=fin, nhid=D, nclass=D, nheads=C, dropout=0.1)
+    fus = [edis.FuseLayer(args, C, nfeat=D), edis.FuseLayer(args, C, nfeat=D)]
+    clf = [edis.MLP(in_feat=D + fin, hidden_size=D, out_size=C, layers=2),
+           edis.MLP(in_feat=2 * D, hidden_size=D, out_size=C, layers=2)]
+    for m in [enc] + fus + clf:
+        m.eval()
+    return args, enc, fus, clf
+
+
+def state_checksum(mods):
+    return sum(float(v.double().abs().sum()) for m in mods for v in m.state_dict().values())
+
+
+def pair_sets(ds, idx, n, labels):
+    """The reference's sampled pair sets, replayed by the bit-exact streaming sampler."""
+    torch.manual_seed(SEED)
+    np.random.seed(SEED)
+    sup = sampler.sample_pairs(n, idx)
+    homo, het = sampler.homo_hetero_split(idx, labels.numpy())
+    torch.manual_seed(SEED + 1)
+    np.random.seed(SEED + 1)
+    dis = [sampler.sample_pairs(n, homo), sampler.sample_pairs(n, het)]
+    return sup, dis
+
+
+@pytest.mark.parametrize("ds", ["cora", "chameleon", "cora_full"])
+def test_inputs_and_ssl_pair_sets_are_the_references(ds):
+    """CPU-side (bit-exact): processed adjacency, normalised features and the SupEdge / DisEdge pair sets
+    of the reference's own `sample_train` on the bundled graphs (pretrainer.py:683-707, 552-574)."""
+    g = load("bundled_ref")
+    adj, x, labels = dataset(ds)
+    idx = adj.indices().numpy()
+    assert idx.shape[1] == int(g[ds + ".e"]) and sha(idx) == str(g[ds + ".indices_sha"])
+    assert sha(x.numpy()) == str(g[ds + ".x_sha"])
+    sup, dis = pair_sets(ds, idx, adj.shape[0], labels)
+    assert sup[0].shape[1] == int(g[ds + ".sup_m"])
+    assert sha(sup[0]) == str(g[ds + ".sup_pairs_sha"]) and sha(sup[1]) == str(g[ds + ".sup_label_sha"])
+    for k in range(2):
+        assert dis[k][0].shape[1] == int(g[ds + ".dis%d_m" % k])
+        assert sha(dis[k][0]) == str(g[ds + ".dis%d_pairs_sha" % k])
+        assert sha(dis[k][1]) == str(g[ds + ".dis%d_label_sha" % k])
+
+
+def oracle_run(enc, fus, clf, x, idx, att, gnn, sup, dis, R, dtype):
+    """Forward + backward of the whole objective on the CPU oracle in `dtype`."""
+    cast = lambda v: v.detach().cpu().clone().to(dtype)
+    p = {k: cast(v).requires_grad_(True) for k, v in enc.state_dict().items() if k.startswith("attention")}
+    fp = [{k: cast(v) for k, v in f.state_dict().items()} for f in fus]
+    mp = [{k: cast(v) for k, v in m.state_dict().items()} for m in clf]
+    aux = [torch.from_numpy(sup[0]), torch.from_numpy(dis[0][0]), torch.from_numpy(dis[1][0])]
+    r = od.disgat_traverse(p, fp, x.to(dtype), torch.from_numpy(idx), C, att, gnn, aux=aux)
+    y = [torch.from_numpy(sup[1]).to(dtype), torch.from_numpy(dis[0][1]).to(dtype), torch.from_numpy(dis[1][1]).to(dtype)]
+    l_sup = od.supedge_loss([[[h[0]] for h in lay] for lay in r["aux"]], y[0])
+    l_dis = od.disedge_loss([[[h[1], h[2]] for h in lay] for lay in r["aux"]], y[1:])
+    l_dif = od.difhead_loss(r["edge_em"], mp)
+    l_em = (r["feats"][-1] * R.to(dtype)).sum()
+    (l_em + 100.0 * l_sup + 100.0 * l_dis + l_dif).backward()
+    return r, (l_sup, l_dis, l_dif), p
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ds,att,gnn", COMBOS)
+def test_bundled_graph_parity(ds, att, gnn):
+    g = load("bundled_ref")
+    k = "%s.a%d_%s." % (ds, att, gnn)
+    adj, x, labels = dataset(ds)
+    idx = adj.indices().numpy()
+    n, fin = adj.shape[0], x.shape[1]
+    args, enc, fus, clf = build_edis(att, gnn, fin)
+    assert abs(state_checksum([enc] + fus + clf) - float(g[k + "state_checksum"])) < 1e-6 * float(g[k + "state_checksum"])
+    sup, dis = pair_sets(ds, idx, n, labels)
+    R = torch.randn(n, D, generator=torch.Generator().manual_seed(3))
+
+    # ---- CUDA path: one traversal with the three pair sets, the reference's objective, backward
+    for m in [enc] + fus + clf:
+        m.to(DEV)
+    graph = edis.Graph(n, idx[0], idx[1], device=DEV)
+    xd = x.to(DEV)
+    pairs = [torch.from_numpy(sup[0]).to(DEV), torch.from_numpy(dis[0][0]).to(DEV), torch.from_numpy(dis[1][0]).to(DEV)]
+    ys = [torch.from_numpy(sup[1]).to(DEV), torch.from_numpy(dis[0][1]).to(DEV), torch.from_numpy(dis[1][1]).to(DEV)]
+    r = enc.traverse(xd, graph, fus, aux=pairs)
+    half = int(C / 2)
+    l_sup = sum(Fn.SslWmse.apply(r["aux"][l][0], ys[0], int((ys[0] != 0).sum())) for l in range(2))
+    l_dis = sum(Fn.SslWmse.apply(r["aux"][l][1][:, :half].contiguous(), ys[1], int((ys[1] != 0).sum()))
+                + Fn.SslWmse.apply(r["aux"][l][2][:, half:].contiguous(), ys[2], int((ys[2] != 0).sum())) for l in range(2))
+    l_dif = 0.0
+    for l in range(2):
+        for c in range(C):
+            em = torch.cat((r["x_in"][l], r["out"][l][:, c * D:(c + 1) * D]), -1)
+            l_dif = l_dif + Fn.NllConstLabel.apply(clf[l](em), c)
+    l_em = (r["x_last"] * R.to(DEV)).sum()
+    (l_em + 100.0 * l_sup + 100.0 * l_dis + l_dif).backward()
+    torch.cuda.synchronize()
+
+    # ---- the reference's samples (fixed edges / nodes) -------------------------------------
+    sel_e, sel_n = g[ds + ".sel_e"], g[ds + ".sel_n"]
+    rows = torch.from_numpy(idx[0]).to(DEV)
+    for l in range(2):
+        e = r["edge_e"][l]
+        assert rel_err(e[sel_e].cpu(), g[k + "e%d" % l], floor=float(g[k + "e%d_absmax" % l])) <= RT, "edge_e vs reference"
+        w = torch.exp(torch.sigmoid(e))
+        alpha = w / torch.zeros(n, C, device=DEV).index_add_(0, rows, w)[rows]
+        assert rel_err(alpha[sel_e].cpu(), g[k + "alpha%d" % l], floor=1.0) <= RT, "alpha vs reference"
+        assert rel_err(r["out"][l][sel_n].cpu(), g[k + "out%d" % l], floor=float(g[k + "out%d_absmax" % l])) <= RT, "out vs reference"
+    assert rel_err(r["x_last"][sel_n].cpu(), g[k + "feat2"], floor=float(g[k + "feat2_absmax"])) <= RT, "feature_2 vs reference"
+    for name, got in (("sup", l_sup), ("dis", l_dis), ("dif", l_dif)):
+        ref = float(g[k + "loss_" + name])
+        assert abs(float(got) - ref) <= RT * abs(ref), "loss_%s: %r vs reference %r" % (name, float(got), ref)
+
+    # ---- the oracle over ALL entries (fp32), gradients arbitrated by its float64 run ---------
+    xc = x.clone()
+    o32, l32, p32 = oracle_run(enc, fus, clf, xc, idx, att, gnn, sup, dis, R, torch.float32)
+    o64, l64, p64 = oracle_run(enc, fus, clf, xc, idx, att, gnn, sup, dis, R, torch.float64)
+    for l in range(2):
+        e_ref = torch.cat(o32["edge_e"][l], 1)
+        assert rel_err(r["edge_e"][l].cpu(), e_ref) <= RT, "edge_e layer %d" % l
+        out_ref = torch.cat([em[:, -D:] for em in o32["edge_em"][l]], 1)
+        assert rel_err(r["out"][l].cpu(), out_ref) <= RT, "elu(h') layer %d" % l
+        al_ref = torch.cat([od.sp_softmax(torch.from_numpy(idx), torch.sigmoid(ec), n) for ec in o32["edge_e"][l]], 1)
+        w = torch.exp(torch.sigmoid(r["edge_e"][l]))
+        alpha = w / torch.zeros(n, C, device=DEV).index_add_(0, rows, w)[rows]
+        assert rel_err(alpha.cpu(), al_ref, floor=1.0) <= RT, "alpha layer %d" % l
+        for s in range(3):
+            aux_ref = torch.cat([o32["aux"][l][c][s] for c in range(C)], 1)
+            assert rel_err(r["aux"][l][s].cpu(), aux_ref) <= RT, "pair logits layer %d set %d" % (l, s)
+    assert rel_err(r["x_last"].cpu(), o32["feats"][-1]) <= RT
+    for got, ref in zip((l_sup, l_dis, l_dif), l32):
+        assert abs(float(got) - float(ref)) <= RT * abs(float(ref))
+    worst = {}
+    gmax = max(float(v.grad.abs().max()) for v in p64.values() if v.grad is not None)
+    for name, prm in enc.named_parameters():
+        if p32[name].grad is None:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
+            continue
+        floor = 1e-3 * gmax
+        tol = max(2e-5, 16.0 * rel_err(p32[name].grad, p64[name].grad, floor))
+        err = rel_err(prm.grad.cpu(), p64[name].grad, floor)
+        assert err <= tol, "grad %s: %.3e > %.3e" % (name, err, tol)
+        worst[name] = err
+    assert worst

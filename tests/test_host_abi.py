@@ -146,3 +146,74 @@ def test_rand_hits_replays_torch_cpu_generator_bit_exactly(seed, n, thr):
     got = bernoulli_hits(n * n, thr)
     assert got is not None and np.array_equal(got, ref_key)
     assert torch.equal(torch.rand(7), after_ref)
+
+
+def test_load_data_refuses_missing_features_unless_opted_in(monkeypatch, tmp_path):
+    """data_load.py:36 fails on a missing feature file; so does the drop-in.  Label-derived synthetic
+    features are an explicit opt-in (EDIS_SYNTH_FEATURES=1) for benchmarks / tests only."""
+    from edgedisentangle_ssl_b200 import data_load
+    from edgedisentangle_ssl_b200.utils import get_parser
+    args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--dataset=cora"])
+    path = os.path.join(ROOT, "data", "cora") + "/"
+    monkeypatch.delenv("EDIS_SYNTH_FEATURES", raising=False)
+    with pytest.raises(FileNotFoundError):
+        data_load.load_data(args, path=path, dataset="cora", edge_type=1)
+    monkeypatch.setenv("EDIS_SYNTH_FEATURES", "1")
+    adj, feats, labels = data_load.load_data(args, path=path, dataset="cora", edge_type=1)
+    assert feats.shape == (2708, 64) and adj.shape == (2708, 2708)
+
+
+def test_load_data_cache_round_trip_and_stale_input(monkeypatch, tmp_path):
+    """EDIS_CACHE_DIR: the processed adjacency is cached keyed by the raw input file's bytes; a second
+    load returns identical tensors from the cache, and a changed input file gets a new key (no stale hit)."""
+    import shutil
+    from edgedisentangle_ssl_b200 import data_load
+    from edgedisentangle_ssl_b200.utils import get_parser
+    ds = tmp_path / "cham"
+    shutil.copytree(os.path.join(ROOT, "data", "chameleon"), ds)
+    cache = tmp_path / "cache"
+    monkeypatch.setenv("EDIS_CACHE_DIR", str(cache))
+    args = get_parser().parse_args(["--model=DISGAT", "--sparse", "--dataset=chameleon"])
+    a1, _, _ = data_load.load_data(args, path=str(ds) + "/", dataset="chameleon", edge_type=1)
+    files = sorted(os.listdir(cache))
+    assert len(files) == 1 and files[0].startswith("adj_1_")
+    a2, _, _ = data_load.load_data(args, path=str(ds) + "/", dataset="chameleon", edge_type=1)
+    assert torch.equal(a1.coalesce().indices(), a2.coalesce().indices())
+    assert torch.equal(a1.coalesce().values(), a2.coalesce().values())
+    edge = np.load(ds / "adj_1.npy")
+    np.save(ds / "adj_1.npy", edge[:-7])                       # the input changes -> new key, rebuilt
+    a3, _, _ = data_load.load_data(args, path=str(ds) + "/", dataset="chameleon", edge_type=1)
+    assert len(os.listdir(cache)) == 2 and a3._nnz() != a1._nnz()
+
+
+def test_header_compiles_as_c_and_struct_layout(tmp_path):
+    """include/edis.h is a C header (no CUDA / C++ needed to bind it): compile a C translation unit
+    against it, independent of _lib.py, and pin the edis_layer_desc layout binders rely on."""
+    import subprocess
+    src = tmp_path / "abi_check.c"
+    src.write_text('''
+#include <stddef.h>
+#include "edis.h"
+_Static_assert(sizeof(edis_layer_desc) == 40, "edis_layer_desc must be 40 bytes");
+_Static_assert(offsetof(edis_layer_desc, att) == 0 && offsetof(edis_layer_desc, C) == 4, "att, C");
+_Static_assert(offsetof(edis_layer_desc, D) == 8 && offsetof(edis_layer_desc, Dv) == 12, "D, Dv");
+_Static_assert(offsetof(edis_layer_desc, training) == 16 && offsetof(edis_layer_desc, p) == 20, "training, p");
+_Static_assert(offsetof(edis_layer_desc, seed) == 24, "seed");
+_Static_assert(offsetof(edis_layer_desc, flags) == 32 && offsetof(edis_layer_desc, reserved) == 36, "flags");
+/* every entry point must be declared with a prototype a C caller can take the address of */
+static const void* table[] = {
+  (const void*)edis_last_error, (const void*)edis_version, (const void*)edis_build_adjacency_host,
+  (const void*)edis_graph_create, (const void*)edis_graph_create_rect, (const void*)edis_graph_destroy,
+  (const void*)edis_graph_info, (const void*)edis_graph_export, (const void*)edis_graph_workspace_bytes,
+  (const void*)edis_edge_list_key, (const void*)edis_graph_save, (const void*)edis_graph_load,
+  (const void*)edis_disga_fwd, (const void*)edis_disga_bwd, (const void*)edis_disga_bwd_dst,
+  (const void*)edis_disga_bwd_src, (const void*)edis_pair_score_fwd, (const void*)edis_pair_score_bwd,
+  (const void*)edis_ssl_wmse_fwd, (const void*)edis_ssl_wmse_bwd };
+int main(void) { return table[0] == 0; }
+''')
+    lib_dir = os.path.join(ROOT, "edgedisentangle_ssl_b200")
+    exe = tmp_path / "abi_check"
+    cmd = ["gcc", "-std=c11", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+           "-L", lib_dir, "-l:libedis.so", "-Wl,-rpath," + lib_dir]
+    p = subprocess.run(cmd, capture_output=True, text=True)
+    assert p.returncode == 0, p.stderr

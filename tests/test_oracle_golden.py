@@ -12,7 +12,7 @@ import torch
 
 from oracle import disgat as od
 from oracle import graph as og
-from helpers import load, t, assert_close, params_from, GOLDEN
+from helpers import load, t, assert_close, params_from, rel_err, GOLDEN
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -191,3 +191,33 @@ def test_first_step_losses_and_grads(tag):
             assert_close(prm.grad, g[key], rtol=2e-5, what=key)
     for k, prm in fus[0].items():
         assert_close(prm.grad, g["cls.fuse1grad." + k], rtol=2e-5, what="fuse1 " + k)
+
+
+# ------------------------------------------------------------------ bundled graphs (BASELINE configs)
+@pytest.mark.parametrize("ds,att,gnn", [("cora", 3, "AT"), ("chameleon", 3, "AT"), ("chameleon", 1, "SAGE"),
+                                        ("chameleon", 2, "GCN")])
+def test_oracle_on_bundled_graphs_vs_reference_samples(ds, att, gnn):
+    """The oracle against what the UNMODIFIED reference produced on the bundled graphs with the same
+    seeded weights (tests/golden/bundled_ref.npz): logits / alpha at 512 fixed edges, elu(h') and
+    feature_2 at 64 fixed nodes.  (The CUDA path is checked against both in tests/test_gpu_bundled.py.)"""
+    import test_gpu_bundled as tb
+    g = load("bundled_ref")
+    k = "%s.a%d_%s." % (ds, att, gnn)
+    adj, x, labels = tb.dataset(ds)
+    idx = adj.indices().numpy()
+    n = adj.shape[0]
+    args, enc, fus, clf = tb.build_edis(att, gnn, x.shape[1])
+    assert abs(tb.state_checksum([enc] + fus + clf) - float(g[k + "state_checksum"])) < 1e-6 * float(g[k + "state_checksum"])
+    p = {kk: v.detach().clone() for kk, v in enc.state_dict().items() if kk.startswith("attention")}
+    fp = [{kk: v.detach().clone() for kk, v in f.state_dict().items()} for f in fus]
+    with torch.no_grad():
+        r = od.disgat_traverse(p, fp, x, torch.from_numpy(idx), tb.C, att, gnn)
+    sel_e, sel_n = g[ds + ".sel_e"], g[ds + ".sel_n"]
+    for l in range(2):
+        e = torch.cat(r["edge_e"][l], 1)
+        assert rel_err(e[sel_e], g[k + "e%d" % l], floor=float(g[k + "e%d_absmax" % l])) <= 1e-5
+        al = torch.cat([od.sp_softmax(torch.from_numpy(idx), torch.sigmoid(ec), n) for ec in r["edge_e"][l]], 1)
+        assert rel_err(al[sel_e], g[k + "alpha%d" % l], floor=1.0) <= 1e-5
+        out = torch.cat([em[:, -tb.D:] for em in r["edge_em"][l]], 1)
+        assert rel_err(out[sel_n], g[k + "out%d" % l], floor=float(g[k + "out%d_absmax" % l])) <= 1e-5
+    assert rel_err(r["feats"][-1][sel_n], g[k + "feat2"], floor=float(g[k + "feat2_absmax"])) <= 1e-5
