@@ -257,9 +257,11 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd(const LayerArgs A)
           const float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
 #pragma unroll
           for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+            // hpre keeps the aggregate BEFORE the bias: the backward needs <gh, agg> and recomputing
+            // agg as (agg + b) - b would put a cancellation into the softmax gradient
             float v = acc[r] * inv;
-            if (A.bias) v += br[r];
             hp[r] = v;
+            if (A.bias) v += br[r];
             o[r] = v > 0.0f ? v : expm1f(v);
           }
         }
@@ -330,8 +332,8 @@ __global__ void k_combine_fwd(const SplitRow* split, int64_t n_split, const floa
     hpre[o] = den > 0.0f ? acc / den : 0.0f;
   } else {
     float v = ws > 0.0f ? acc / ws : 0.0f;
+    hpre[o] = v;                       // pre-bias aggregate (see k_disga_fwd)
     if (bias) v += bias[x];
-    hpre[o] = v;
     out[o] = v > 0.0f ? v : expm1f(v);
   }
   if (x < 2 * C) stats[static_cast<int64_t>(s.row) * 2 * C + x] = sx;
@@ -419,9 +421,9 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst(const Laye
       for (int k = 0; k < NCH; ++k) tpart[k] = 0.0f;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        dh[r] = hp[r] > 0.0f ? go[r] : go[r] * expf(hp[r]);
-        const float agg = A.bias ? hp[r] - br[r] : hp[r];
-        tpart[r / RPC] = fmaf(dh[r], agg, tpart[r / RPC]);
+        const float v = A.bias ? hp[r] + br[r] : hp[r];      // same fp32 op as the forward: bit-identical
+        dh[r] = v > 0.0f ? go[r] : go[r] * expf(v);
+        tpart[r / RPC] = fmaf(dh[r], hp[r], tpart[r / RPC]);
       }
       if (first_chunk) T::store(A.gh + rowoff, dh, lane, A.D);
       tc = T::reduce_own(tpart, lane);

@@ -370,6 +370,22 @@ class SageFused(torch.autograd.Function):
                 None, None, None, None)
 
 
+# Node count from which the layer projection runs as 3xTF32 on the tensor cores instead of the fp32 SIMT
+# GEMM.  3xTF32 carries ~2^-21 relative error (dropped xl*Wl term + the TF32 rounding of the low parts)
+# against ~2^-24 sqrt(F) for fp32: forward values stay inside 1e-5, but WEIGHT GRADIENTS measured against a
+# float64 evaluation move from < 2e-5 to 7e-5 on cora_full (tests/test_gpu_bundled.py) -- a logit's
+# gradient is discontinuous at P_i + Q_j = 0 (leaky-relu kink), so a few more sign flips near zero show up
+# there.  Below this size the GEMM is a negligible part of the step, so the exact one is used; above it
+# (EDIS_PROJ3X=1 forces it on everywhere, =0 off) the projection would otherwise be 15 % of the step.
+PROJ3X_MIN_ROWS = 65536
+
+
+def use_proj3x(n_rows):
+    import os
+    mode = os.environ.get("EDIS_PROJ3X", "auto")
+    return mode == "1" or (mode != "0" and n_rows >= PROJ3X_MIN_ROWS)
+
+
 def _tf32_hi(t):
     """Round-to-nearest onto the TF32 grid (10 explicit mantissa bits), result still fp32."""
     return ((t.view(torch.int32) + 0x1000) & -0x2000).view(torch.float32)

@@ -18,7 +18,8 @@ from torch import nn
 from torch.nn.parameter import Parameter
 
 from . import _lib
-from .functional import ChannelLinear, DisGAFused, PairList, PairScore, Proj3xTF32, SageFused, node_linear
+from .functional import (ChannelLinear, DisGAFused, PairList, PairScore, Proj3xTF32, SageFused, node_linear,
+                         use_proj3x)
 from .graph import as_graph
 
 _seed_counter = itertools.count(1)
@@ -103,7 +104,7 @@ def run_channels(chs, x, graph, aux=None, aggregate=True, aux_ranges=None):
     if aggregate and not use_agg:
         w_val = [torch.cat([(l.W_em if gnn == "AT" else l.ag_layer.weight) for l in chs], 1)]
     w_all = torch.cat(w_score + w_val, 1)
-    if os.environ.get("EDIS_PROJ3X", "1") != "0" and x.shape[0] >= 4096:
+    if use_proj3x(x.shape[0]):
         proj = Proj3xTF32.apply(x, w_all)             # fp32-accurate 3xTF32 split on the tensor cores
     else:
         proj = x @ w_all                              # one fp32 GEMM (TF32 off) for all channels / operands
@@ -174,7 +175,7 @@ def _maybe_recompute(proj, x, w_all, lean):
             return contextlib.nullcontext()
     key, shape = proj.data_ptr(), proj.shape
     xd, wd = x.detach(), w_all.detach()
-    use3x = os.environ.get("EDIS_PROJ3X", "1") != "0" and x.shape[0] >= 4096
+    use3x = use_proj3x(x.shape[0])
 
     def pack(t):
         return _Recompute if (t.data_ptr() == key and t.shape == shape) else t

@@ -248,8 +248,8 @@ def _edis_kernels():
 def _project(x, w):
     """Node projection at fp32 accuracy: 3xTF32 on the tensor cores for big node counts (see
     functional.Proj3xTF32), plain fp32 otherwise (and always on CPU)."""
-    if x.is_cuda and x.shape[0] >= 4096 and os.environ.get("EDIS_PROJ3X", "1") != "0":
-        from .functional import _mm_3xtf32
+    from .functional import _mm_3xtf32, use_proj3x
+    if x.is_cuda and use_proj3x(x.shape[0]):
         return _mm_3xtf32(x, w)
     return x @ w
 

@@ -144,7 +144,8 @@ typedef struct {
 
 /* Forward.  Saved for backward: edge_e[E,C], stats[N,2C] (row sums: sum w, sum w*mask), hpre and,
  * for att 3, esign.
- * out / hpre: [N, C*Dv] contiguous.  workspace >= edis_graph_workspace_bytes(g, C*Dv + 2*C).
+ * out / hpre: [N, C*Dv] contiguous (hpre = the aggregate BEFORE bias and ELU, out = elu(hpre + bias)).
+ * workspace >= edis_graph_workspace_bytes(g, C*Dv + 2*C).
  *   esign  att 3 only, edis_disga_sign_bytes(g, d) bytes or NULL (inference: nothing is saved):
  *          one SIGN BIT per element of P_i + Q_j for every edge.  Leaky-relu is piecewise linear,
  *          so both backward passes need only lrelu'(z), never z: the destination pass reads 64 B

@@ -119,6 +119,19 @@ def oracle_run(enc, fus, clf, x, idx, att, gnn, sup, dis, R, dtype):
 @pytest.mark.gpu
 @pytest.mark.parametrize("ds,att,gnn", COMBOS)
 def test_bundled_graph_parity(ds, att, gnn):
+    run_parity(ds, att, gnn, grad_cap=0.0)
+
+
+@pytest.mark.gpu
+def test_bundled_graph_parity_with_3xtf32_projection_forced(monkeypatch):
+    """cora_full with the tensor-core 3xTF32 projection forced on (default only from 65536 nodes up,
+    functional.PROJ3X_MIN_ROWS): forward values still inside 1e-5; weight gradients within 2e-4 of the float64
+    arbiter (measured 7e-5: ~2^-21 GEMM error + sign flips at the leaky-relu kink) -- the documented price."""
+    monkeypatch.setenv("EDIS_PROJ3X", "1")
+    run_parity("cora_full", 3, "AT", grad_cap=2e-4)
+
+
+def run_parity(ds, att, gnn, grad_cap):
     g = load("bundled_ref")
     k = "%s.a%d_%s." % (ds, att, gnn)
     adj, x, labels = dataset(ds)
@@ -163,7 +176,7 @@ def test_bundled_graph_parity(ds, att, gnn):
     assert rel_err(r["x_last"][sel_n].cpu(), g[k + "feat2"], floor=float(g[k + "feat2_absmax"])) <= RT, "feature_2 vs reference"
     for name, got in (("sup", l_sup), ("dis", l_dis), ("dif", l_dif)):
         ref = float(g[k + "loss_" + name])
-        assert abs(float(got) - ref) <= RT * abs(ref), "loss_%s: %r vs reference %r" % (name, float(got), ref)
+        assert abs(float(got.detach()) - ref) <= RT * abs(ref), "loss_%s: %r vs reference %r" % (name, float(got.detach()), ref)
 
     # ---- the oracle over ALL entries (fp32), gradients arbitrated by its float64 run ---------
     xc = x.clone()
@@ -183,15 +196,17 @@ def test_bundled_graph_parity(ds, att, gnn):
             assert rel_err(r["aux"][l][s].cpu(), aux_ref) <= RT, "pair logits layer %d set %d" % (l, s)
     assert rel_err(r["x_last"].cpu(), o32["feats"][-1]) <= RT
     for got, ref in zip((l_sup, l_dis, l_dif), l32):
-        assert abs(float(got) - float(ref)) <= RT * abs(float(ref))
+        assert abs(float(got.detach()) - float(ref.detach())) <= RT * abs(float(ref.detach()))
     worst = {}
     gmax = max(float(v.grad.abs().max()) for v in p64.values() if v.grad is not None)
     for name, prm in enc.named_parameters():
+        if name not in p32:            # the encoder's own (unused, is_specific) fusers
+            continue
         if p32[name].grad is None:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0
             continue
         floor = 1e-3 * gmax
-        tol = max(2e-5, 16.0 * rel_err(p32[name].grad, p64[name].grad, floor))
+        tol = max(2e-5, 16.0 * rel_err(p32[name].grad, p64[name].grad, floor), grad_cap)
         err = rel_err(prm.grad.cpu(), p64[name].grad, floor)
         assert err <= tol, "grad %s: %.3e > %.3e" % (name, err, tol)
         worst[name] = err
