@@ -9,5 +9,6 @@ from . import _lib  # noqa: F401  (raises ImportError if libedis.so is missing)
 from .graph import Graph, build_adjacency, as_graph  # noqa: F401
 from .layers import DisGALayer, FuseLayer, SageConv, GraphConvolution, run_channels  # noqa: F401
 from .models import DISGAT, MLP  # noqa: F401
+from .baselines import GraphAttentionLayer, DisentangleLayer  # noqa: F401
 
 __version__ = "0.1"

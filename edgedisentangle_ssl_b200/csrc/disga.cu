@@ -58,11 +58,22 @@
 #ifndef EDIS_PF_SRC
 #define EDIS_PF_SRC 0
 #endif
+// ring (bulk-copy) variants: slots per warp
+#ifndef EDIS_NS_DST
+#define EDIS_NS_DST 4
+#endif
+#ifndef EDIS_NS_SRC
+#define EDIS_NS_SRC 4
+#endif
+#ifndef EDIS_NS_FWD
+#define EDIS_NS_FWD 3
+#endif
 
 namespace edis {
 
 struct LayerArgs {
   const Item* items;
+  int64_t n_edges;          // edges of the pass's index (CSR or CSC): items cover [0, n_edges) in order
   int64_t n_units;          // items * G
   int G;                    // channel groups per item
   const int32_t* nbr;       // CSR col (dst pass / fwd) or CSC row (src pass)
@@ -553,11 +564,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst(const Laye
                 if (T::own_ch(lane) == cc) gdot = gp;
               }
             }
-            const float s = sigmoid_mufu(ev[u]);
+            float s, sp;
+            sigmoid_pair(ev[u], s, sp);
             const float alpha = exp_mufu(s) * inv;
             const float ms = A.training ? keep_scale(A.seed, edge * A.C + myc, A.p, A.inv_keep) : 1.0f;
             const float ds = alpha * (gdot * ms - tc);
-            const float de = valid ? fmaf(ds, s * (1.0f - s), gx[u]) : 0.0f;
+            const float de = valid ? fmaf(ds, sp, gx[u]) : 0.0f;
             if (T::own_writer(lane) && valid) {
               st_stream(A.edge_rec + edge * 2 * A.C + myc, alpha * ms);
               st_stream(A.edge_rec + edge * 2 * A.C + A.C + myc, de);
@@ -804,6 +816,498 @@ __global__ void __launch_bounds__(256) k_sage_bwd_src_x(const LayerArgs A) {
   }
 }
 
+// ------------------------------------------------------------------ ring (1-D TMA) variants
+// Same math as the kernels above for the layouts where one warp owns a node's WHOLE row (att 3,
+// per-channel operand, C == channels per warp: C = 8 / 4 / 2 at D = 64), restructured around
+// asynchronous bulk copies:
+//   * every warp owns a CONTIGUOUS run of work items (and therefore of edges), balanced by
+//     edges + kRowCost * rows, found by binary search on the item list -- so its gathers can run
+//     ahead across row boundaries (median in-degree of a power-law graph is ~9: per-row pipeline
+//     restarts were most of the exposed latency);
+//   * lane 0 issues ONE cp.async.bulk per gathered row (2 KB of V_j / gh_i, 4 KB of Q_j | V_j) into
+//     a private shared-memory ring of NS slots, NS edges ahead, each slot with its own mbarrier;
+//     the warp waits on the slot's phase and reads the row with LDS.128.  Compared with the per-lane
+//     LDG.128 path: 1 instruction instead of 16 LDG + 64-bit address chains per edge, no staging
+//     registers held across the DRAM latency, and NS rows per warp in flight independent of the
+//     consumer's progress.
+#ifndef EDIS_ROW_COST
+#define EDIS_ROW_COST 6
+#endif
+#ifndef EDIS_RPW
+#define EDIS_RPW 4
+#endif
+constexpr int kRowCost = EDIS_ROW_COST;   // cost of one work item in units of edges (row prologue / epilogue)
+constexpr int kRangesPerWarp = EDIS_RPW;  // contiguous runs per warp (tail balance vs pipeline restarts)
+
+struct WarpRange {
+  int64_t i0, i1;   // items [i0, i1)
+};
+// first item whose cost prefix  beg_i + kRowCost * i  is >= target  (items are in edge order)
+__device__ __forceinline__ int64_t item_lower_bound(const Item* items, int64_t n_items, int64_t target) {
+  int64_t lo = 0, hi = n_items;
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    const int64_t c = static_cast<int64_t>(__ldg(&items[mid].beg)) + kRowCost * mid;
+    if (c < target) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+__device__ __forceinline__ WarpRange warp_range(const LayerArgs& A, int64_t rg, int64_t n_ranges) {
+  const int64_t total = A.n_edges + kRowCost * A.n_units;
+  const int64_t lo = total / n_ranges * rg + min(rg, total % n_ranges);
+  const int64_t hi = total / n_ranges * (rg + 1) + min(rg + 1, total % n_ranges);
+  WarpRange r;
+  r.i0 = item_lower_bound(A.items, A.n_units, lo);
+  r.i1 = rg + 1 == n_ranges ? A.n_units : item_lower_bound(A.items, A.n_units, hi);
+  return r;
+}
+
+// Per-warp producer / consumer state of the ring.  ROWB = bytes per slot.
+template <int NS, int ROWB>
+struct Ring {
+  unsigned char* slots;
+  uint32_t bar0;         // shared-space address of this warp's first mbarrier
+  uint32_t slot0;        // shared-space address of this warp's first slot
+  uint32_t kp, kc;       // rows issued / rows consumed so far (slot = k % NS, phase parity = (k / NS) & 1)
+  __device__ __forceinline__ void init(unsigned char* dyn, int wid, int lane) {
+    slots = dyn + static_cast<size_t>(wid) * NS * ROWB;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(dyn + static_cast<size_t>(8) * NS * ROWB) + wid * NS;
+    bar0 = smem_u32(bars);
+    slot0 = smem_u32(slots);
+    kp = kc = 0;
+    if (lane == 0) {
+#pragma unroll
+      for (int s = 0; s < NS; ++s) mbar_init(bar0 + 8 * s, 1);
+    }
+    mbar_fence_init();
+    __syncwarp();
+  }
+  __device__ __forceinline__ const unsigned char* wait_next() {      // all lanes
+    const uint32_t s = kc % NS;
+    mbar_wait(bar0 + 8 * s, (kc / NS) & 1u);
+    ++kc;
+    return slots + s * ROWB;
+  }
+};
+
+// Neighbour ids of the 32-edge blocks the consumer (block b0) and the producer (b0 or b0 + 1) are in.
+struct NbrWindow {
+  int64_t b0;
+  int j0, j1;
+  __device__ __forceinline__ void load(const int32_t* nbr, int64_t n_edges, int64_t e, int lane) {
+    b0 = e >> 5;
+    const int64_t i0 = (b0 << 5) + lane, i1 = i0 + 32;
+    j0 = i0 < n_edges ? __ldg(nbr + i0) : 0;
+    j1 = i1 < n_edges ? __ldg(nbr + i1) : 0;
+  }
+  __device__ __forceinline__ void advance_to(const int32_t* nbr, int64_t n_edges, int64_t e, int lane) {
+    if ((e >> 5) != b0) {
+      b0 = e >> 5;
+      j0 = j1;
+      const int64_t i1 = (b0 << 5) + 32 + lane;
+      j1 = i1 < n_edges ? __ldg(nbr + i1) : 0;
+    }
+  }
+  __device__ __forceinline__ int at(int64_t e) const {      // e in block b0 or b0 + 1; all lanes
+    return __shfl_sync(FULL, (e >> 5) == b0 ? j0 : j1, static_cast<int>(e & 31));
+  }
+};
+
+// backward, destination pass (att 3, per-channel operand, whole-row warps): ring of V_j rows
+template <class T, int NS>
+__global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const LayerArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC;
+  constexpr int ROWB = R * 128;         // C * D * 4 bytes with C == T::CPW
+  constexpr int SBPL = (R + 7) / 8;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ float s_da[8 * 32 * R];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  Ring<NS, ROWB> ring;
+  ring.init(dyn_smem, wid, lane);
+  float* my_da = s_da + wid * 32 * R + lane;
+#pragma unroll
+  for (int r = 0; r < R; ++r) my_da[r * 32] = 0.0f;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  const int64_t n_ranges = nwarps * kRangesPerWarp;
+  const int CD = A.C * A.D;
+  const int myc = T::own_ch(lane);
+  bool touched = false;
+  for (int64_t rg = static_cast<int64_t>(blockIdx.x) * 8 + wid; rg < n_ranges; rg += nwarps) {
+    const WarpRange wr = warp_range(A, rg, n_ranges);
+    if (wr.i0 >= wr.i1) continue;
+    touched = true;
+    const int64_t e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    NbrWindow nw;
+    nw.load(A.nbr, A.n_edges, e0, lane);
+    int64_t pe = e0;
+    auto issue = [&]() {      // all lanes; lane 0 issues the copy of edge pe's source row
+      const int raw = nw.at(pe);
+      if (lane == 0) {
+        const uint32_t s = ring.kp % NS;
+        const uint32_t bar = ring.bar0 + 8 * s;
+        const float* src = A.V + static_cast<int64_t>(raw & kIdMask) * A.ldv;
+        mbar_expect_tx(bar, ROWB);
+        if (is_hot(raw, A.hot_min)) bulk_g2s<true>(ring.slot0 + s * ROWB, src, ROWB, bar);
+        else bulk_g2s<false>(ring.slot0 + s * ROWB, src, ROWB, bar);
+      }
+      ++ring.kp;
+      ++pe;
+    };
+    for (int q = 0; q < NS && pe < e1; ++q) issue();
+    int64_t e = e0;
+    unsigned sg_n = 0u;
+    float ev_n = 0.0f, gx_n = 0.0f;
+    auto load_edge = [&](int64_t ee) {
+      const int64_t so = (ee * 32 + lane) * SBPL;
+      sg_n = SBPL == 1 ? static_cast<unsigned>(ld_stream(A.esign + so))
+                       : static_cast<unsigned>(ld_stream(reinterpret_cast<const unsigned short*>(A.esign + so)));
+      ev_n = ld_stream(A.edge_e + ee * A.C + myc);
+      gx_n = A.g_edge_e ? ld_stream(A.g_edge_e + ee * A.C + myc) : 0.0f;
+    };
+    if (e0 < e1) load_edge(e0);
+    for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
+      const Item it = A.items[item_id];
+      const int64_t srow = static_cast<int64_t>(it.row);
+      const int64_t rowoff = srow * CD;
+      bool first_chunk = it.slot < 0;
+      if (it.slot >= 0) first_chunk = item_id == 0 || A.items[item_id - 1].row != it.row;
+      // the next item's row data (g_out, hpre: 2 x ROWB bytes, consecutive rows) into L2 while this row runs
+      if (item_id + 1 < wr.i1) {
+        const int64_t nrow = static_cast<int64_t>(__ldg(&A.items[item_id + 1].row)) * CD;
+        if (lane < R) prefetch_l2_line<false>(A.g_out + nrow + lane * 32);
+        else if (lane < 2 * R) prefetch_l2_line<false>(A.hpre + nrow + (lane - R) * 32);
+      }
+      float dh[R], tc;
+      const float wsum = __ldg(A.stats + srow * 2 * A.C + myc);
+      const float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
+      {
+        float go[R], hp[R], br[R], tpart[NCH];
+        T::load(go, A.g_out + rowoff, lane, A.D);
+        T::load(hp, A.hpre + rowoff, lane, A.D);
+        if (A.bias) T::load(br, A.bias, lane, A.D);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) tpart[k] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float v = A.bias ? hp[r] + br[r] : hp[r];
+          dh[r] = v > 0.0f ? go[r] : go[r] * expf(v);
+          tpart[r / RPC] = fmaf(dh[r], hp[r], tpart[r / RPC]);
+        }
+        if (first_chunk) T::store(A.gh + rowoff, dh, lane, A.D);
+        tc = T::reduce_own(tpart, lane);
+      }
+      float dP[R], dsum[NCH];
+      zero<T>(dP);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) dsum[k] = 0.0f;
+      for (; e < it.end; ++e) {
+        nw.advance_to(A.nbr, A.n_edges, e, lane);
+        // per-edge streams (coalesced, sequential in e): sign record, logit, upstream logit gradient --
+        // loaded ONE EDGE AHEAD into registers so that their latency hides under this edge's math
+        const unsigned sg = sg_n;
+        const float ev = ev_n, gx = gx_n;
+        if (e + 1 < e1) load_edge(e + 1);
+        const float* sp = reinterpret_cast<const float*>(ring.wait_next());
+        float h[R];
+#pragma unroll
+        for (int k = 0; k < T::KV; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(sp + (k * 32 + lane) * 4);
+          h[4 * k] = v.x; h[4 * k + 1] = v.y; h[4 * k + 2] = v.z; h[4 * k + 3] = v.w;
+        }
+        float gpart[NCH];
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) gpart[k] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) gpart[r / RPC] = fmaf(dh[r], h[r], gpart[r / RPC]);
+        const float gdot = T::reduce_own(gpart, lane);     // shuffles: every lane has consumed its slot reads
+        if (pe < e1) issue();                              // refill the slot just read
+        float s, sgrad;
+        sigmoid_pair(ev, s, sgrad);
+        const float alpha = exp_mufu(s) * inv;
+        const float ms = A.training ? keep_scale(A.seed, e * A.C + myc, A.p, A.inv_keep) : 1.0f;
+        const float ds = alpha * (gdot * ms - tc);
+        const float de = fmaf(ds, sgrad, gx);
+        if (T::own_writer(lane)) {
+          st_stream(A.edge_rec + e * 2 * A.C + myc, alpha * ms);
+          st_stream(A.edge_rec + e * 2 * A.C + A.C + myc, de);
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const float d = T::from_owner(de, k, lane);
+          dsum[k] += d;
+#pragma unroll
+          for (int r = k * RPC; r < (k + 1) * RPC; ++r) dP[r] = fmaf(sign_pos_f<R>(sg, r), d, dP[r]);
+        }
+      }
+      {
+        float pr[R], ar[R];
+        T::load(pr, A.P + srow * A.ldp, lane, A.D);
+        T::load(ar, A.a, lane, A.D);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          dP[r] = fmaf(0.99f, dP[r], 0.01f * dsum[r / RPC]);
+          my_da[r * 32] = fmaf(pr[r], dP[r], my_da[r * 32]);
+          dP[r] *= ar[r];
+        }
+      }
+      if (it.slot < 0) T::store(A.gP + srow * A.ldgp, dP, lane, A.D);
+      else T::store(A.partial + static_cast<int64_t>(it.slot) * A.pwidth, dP, lane, A.D);
+    }
+  }
+  if (touched) {
+    float da[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) da[r] = my_da[r * 32];
+    T::atomic_add(A.ga, da, lane, A.D);
+  }
+}
+
+// backward, source pass (att 3, per-channel operand): ring of {gh_i row, (alpha_drop, d logit) record,
+// sign record} per out-edge of the source row -- the two per-edge records sit at the edge's CSR slot
+// (random 64-byte reads over CSC): they ride the same mbarrier as the row
+template <class T, int NS>
+__global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src_ring(const LayerArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC;
+  constexpr int ROWB = R * 128;
+  constexpr int SBPL = (R + 7) / 8;
+  constexpr int RECB = 2 * T::CPW * 4;          // (alpha_drop, d logit)[2C] floats
+  constexpr int SIGNB = 32 * SBPL;
+  constexpr int SLOTB = ROWB + RECB + SIGNB;
+  static_assert(RECB % 16 == 0 && SIGNB % 16 == 0, "bulk copies move multiples of 16 bytes");
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  __shared__ float s_da[8 * 32 * R];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  Ring<NS, SLOTB> ring;
+  ring.init(dyn_smem, wid, lane);
+  float* my_da = s_da + wid * 32 * R + lane;
+#pragma unroll
+  for (int r = 0; r < R; ++r) my_da[r * 32] = 0.0f;
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  const int64_t n_ranges = nwarps * kRangesPerWarp;
+  const int CD = A.C * A.D;
+  int cidx[NCH];
+#pragma unroll
+  for (int k = 0; k < NCH; ++k) cidx[k] = T::ch(k, lane);
+  bool touched = false;
+  for (int64_t rg = static_cast<int64_t>(blockIdx.x) * 8 + wid; rg < n_ranges; rg += nwarps) {
+    const WarpRange wr = warp_range(A, rg, n_ranges);
+    if (wr.i0 >= wr.i1) continue;
+    touched = true;
+    const int64_t e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    NbrWindow nw, ew;
+    nw.load(A.nbr, A.n_edges, e0, lane);
+    ew.load(A.eid, A.n_edges, e0, lane);
+    int64_t pe = e0;
+    auto issue = [&]() {
+      const int raw = nw.at(pe);
+      const int64_t edge = ew.at(pe);
+      if (lane == 0) {
+        const uint32_t s = ring.kp % NS;
+        const uint32_t bar = ring.bar0 + 8 * s;
+        const uint32_t dst = ring.slot0 + s * SLOTB;
+        const float* src = A.gh + static_cast<int64_t>(raw & kIdMask) * CD;
+        mbar_expect_tx(bar, SLOTB);
+        if (is_hot(raw, A.hot_min)) bulk_g2s<true>(dst, src, ROWB, bar);
+        else bulk_g2s<false>(dst, src, ROWB, bar);
+        bulk_g2s<false>(dst + ROWB, A.edge_rec + edge * 2 * A.C, RECB, bar);
+        bulk_g2s<false>(dst + ROWB + RECB, A.esign + edge * SIGNB, SIGNB, bar);
+      }
+      ++ring.kp;
+      ++pe;
+    };
+    for (int q = 0; q < NS && pe < e1; ++q) issue();
+    int64_t e = e0;
+    for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
+      const Item it = A.items[item_id];
+      if (item_id + 1 < wr.i1 && lane < R)      // next source row's Q_j (row epilogue operand) into L2
+        prefetch_l2_line<false>(A.Q + static_cast<int64_t>(__ldg(&A.items[item_id + 1].row)) * A.ldq + lane * 32);
+      float accV[R], accQ[R], dss[NCH];
+      zero<T>(accV);
+      zero<T>(accQ);
+#pragma unroll
+      for (int k = 0; k < NCH; ++k) dss[k] = 0.0f;
+      for (; e < it.end; ++e) {
+        nw.advance_to(A.nbr, A.n_edges, e, lane);
+        ew.advance_to(A.eid, A.n_edges, e, lane);
+        const unsigned char* sp = ring.wait_next();
+        const float* rowp = reinterpret_cast<const float*>(sp);
+        const float* recp = reinterpret_cast<const float*>(sp + ROWB);
+        float dh[R], ad[NCH], de[NCH];
+#pragma unroll
+        for (int k = 0; k < T::KV; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(rowp + (k * 32 + lane) * 4);
+          dh[4 * k] = v.x; dh[4 * k + 1] = v.y; dh[4 * k + 2] = v.z; dh[4 * k + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          ad[k] = recp[cidx[k]];
+          de[k] = recp[A.C + cidx[k]];
+        }
+        const unsigned sg = SBPL == 1 ? static_cast<unsigned>(sp[ROWB + RECB + lane])
+                                      : static_cast<unsigned>(reinterpret_cast<const unsigned short*>(sp + ROWB + RECB)[lane]);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+#pragma unroll
+          for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+            accV[r] = fmaf(ad[k], dh[r], accV[r]);
+            accQ[r] = fmaf(sign_pos_f<R>(sg, r), de[k], accQ[r]);
+          }
+          dss[k] += de[k];
+        }
+        __syncwarp();                 // every lane has read the slot
+        if (pe < e1) issue();
+      }
+      const int64_t jrow = static_cast<int64_t>(it.row);
+      if (it.end > it.beg) {
+        float qr[R], ar[R];
+        T::load(qr, A.Q + jrow * A.ldq, lane, A.D);
+        T::load(ar, A.a, lane, A.D);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          accQ[r] = fmaf(0.99f, accQ[r], 0.01f * dss[r / RPC]);
+          my_da[r * 32] = fmaf(qr[r], accQ[r], my_da[r * 32]);
+          accQ[r] *= ar[r];
+        }
+      }
+      if (it.slot < 0) {
+        T::store(A.gV + jrow * A.ldgv, accV, lane, A.D);
+        T::store(A.gQ + jrow * A.ldgq, accQ, lane, A.D);
+      } else {
+        float* pb = A.partial + static_cast<int64_t>(it.slot) * A.pwidth;
+        T::store(pb, accV, lane, A.D);
+        T::store(pb + CD, accQ, lane, A.D);
+      }
+    }
+  }
+  if (touched) {
+    float da[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) da[r] = my_da[r * 32];
+    T::atomic_add(A.ga, da, lane, A.D);
+  }
+}
+
+// forward (att 3, per-channel operand): ring of Q_j | V_j (2 rows, contiguous in the projection buffer)
+template <class T, int NS>
+__global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerArgs A) {
+  constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC;
+  constexpr int ROWB = R * 128;
+  constexpr int SLOTB = 2 * ROWB;
+  constexpr int SBPL = (R + 7) / 8;
+  extern __shared__ __align__(128) unsigned char dyn_smem[];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  Ring<NS, SLOTB> ring;
+  ring.init(dyn_smem, wid, lane);
+  const int64_t nwarps = static_cast<int64_t>(gridDim.x) * 8;
+  const int64_t n_ranges = nwarps * kRangesPerWarp;
+  const int CD = A.C * A.D;
+  const int myc = T::own_ch(lane);
+  float ar[R];
+  T::load(ar, A.a, lane, A.D);
+#pragma unroll
+  for (int r = 0; r < R; ++r) ar[r] = -ar[r];
+  for (int64_t rg = static_cast<int64_t>(blockIdx.x) * 8 + wid; rg < n_ranges; rg += nwarps) {
+    const WarpRange wr = warp_range(A, rg, n_ranges);
+    if (wr.i0 >= wr.i1) continue;
+    const int64_t e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    NbrWindow nw;
+    nw.load(A.nbr, A.n_edges, e0, lane);
+    int64_t pe = e0;
+    auto issue = [&]() {
+      const int raw = nw.at(pe);
+      if (lane == 0) {
+        const uint32_t s = ring.kp % NS;
+        const uint32_t bar = ring.bar0 + 8 * s;
+        const float* src = A.Q + static_cast<int64_t>(raw & kIdMask) * A.ldq;      // Q_j | V_j adjacent
+        mbar_expect_tx(bar, SLOTB);
+        if (is_hot(raw, A.hot_min)) bulk_g2s<true>(ring.slot0 + s * SLOTB, src, SLOTB, bar);
+        else bulk_g2s<false>(ring.slot0 + s * SLOTB, src, SLOTB, bar);
+      }
+      ++ring.kp;
+      ++pe;
+    };
+    for (int q = 0; q < NS && pe < e1; ++q) issue();
+    int64_t e = e0;
+    for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
+      const Item it = A.items[item_id];
+      const int64_t srow = static_cast<int64_t>(it.row);
+      if (item_id + 1 < wr.i1 && lane < R)
+        prefetch_l2_line<false>(A.P + static_cast<int64_t>(__ldg(&A.items[item_id + 1].row)) * A.ldp + lane * 32);
+      float pr[R];
+      T::load(pr, A.P + srow * A.ldp, lane, A.D);
+      float acc[R], ws = 0.0f, wms = 0.0f;
+      zero<T>(acc);
+      for (; e < it.end; ++e) {
+        nw.advance_to(A.nbr, A.n_edges, e, lane);
+        const float* sp = reinterpret_cast<const float*>(ring.wait_next());
+        float q[R], h[R];
+#pragma unroll
+        for (int k = 0; k < T::KV; ++k) {
+          const float4 v = *reinterpret_cast<const float4*>(sp + (k * 32 + lane) * 4);
+          q[4 * k] = v.x; q[4 * k + 1] = v.y; q[4 * k + 2] = v.z; q[4 * k + 3] = v.w;
+          const float4 u = *reinterpret_cast<const float4*>(sp + R * 32 + (k * 32 + lane) * 4);
+          h[4 * k] = u.x; h[4 * k + 1] = u.y; h[4 * k + 2] = u.z; h[4 * k + 3] = u.w;
+        }
+        float part[NCH];
+        unsigned mask = 0u;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) part[k] = 0.0f;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const float w = -pr[r] - q[r];
+          mask = sign_push(mask, w);
+          part[r / RPC] = fmaf(ar[r], fminf(w, 0.01f * w), part[r / RPC]);
+        }
+        const float ev = T::reduce_own(part, lane);      // shuffles: q has been consumed by every lane
+        // h is still only in registers of this lane: the slot is free once all lanes have loaded it
+        if (pe < e1) issue();
+        if (A.esign) {
+          const int64_t so = (e * 32 + lane) * SBPL;
+          if (SBPL == 1) st_stream(A.esign + so, static_cast<unsigned char>(mask));
+          else st_stream(reinterpret_cast<unsigned short*>(A.esign + so), static_cast<unsigned short>(mask));
+        }
+        const float w = exp_mufu(sigmoid_mufu(ev));
+        const float ms = A.training ? keep_scale(A.seed, e * A.C + myc, A.p, A.inv_keep) : 1.0f;
+        const float wm = w * ms;
+        ws += w;
+        wms += wm;
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const float wk = T::from_owner(wm, k, lane);
+#pragma unroll
+          for (int r = k * RPC; r < (k + 1) * RPC; ++r) acc[r] = fmaf(wk, h[r], acc[r]);
+        }
+        if (T::own_writer(lane)) st_stream(A.edge_e + e * A.C + myc, ev);
+      }
+      if (it.slot < 0) {
+        float o[R], hp[R], br[R];
+        if (A.bias) T::load(br, A.bias, lane, A.D);
+#pragma unroll
+        for (int k = 0; k < NCH; ++k) {
+          const float wsum = T::from_owner(ws, k, lane);
+          const float inv = wsum > 0.0f ? 1.0f / wsum : 0.0f;
+#pragma unroll
+          for (int r = k * RPC; r < (k + 1) * RPC; ++r) {
+            float v = acc[r] * inv;
+            hp[r] = v;
+            if (A.bias) v += br[r];
+            o[r] = v > 0.0f ? v : expm1f(v);
+          }
+        }
+        T::store(A.hpre + srow * CD, hp, lane, A.D);
+        T::store(A.out + srow * CD, o, lane, A.D);
+      } else {
+        T::store(A.partial + static_cast<int64_t>(it.slot) * A.pwidth, acc, lane, A.D);
+      }
+      if (T::own_writer(lane)) {
+        float* st = it.slot < 0 ? A.stats + srow * 2 * A.C : A.partial + static_cast<int64_t>(it.slot) * A.pwidth + CD;
+        st[myc] = ws;
+        st[A.C + myc] = wms;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------ host dispatch
 enum class Pass { Fwd, BwdDst, BwdSrc };
 
@@ -818,18 +1322,60 @@ static int launch_persistent(K kernel, const edis_graph* g, const LayerArgs& A, 
   return EDIS_OK;
 }
 
+// ring variants: whole-row warps (one channel group), 16-byte aligned rows, D == 64 layouts
+template <class T>
+static bool ring_ok(const LayerArgs& A) {
+  static const int on = env_int("EDIS_RING", 1);
+  return on && T::kRing && A.C == T::CPW && A.D == 64;
+}
+
+template <class K>
+static int launch_ring(K kernel, int slot_bytes_per_warp, const edis_graph* g, const LayerArgs& A, cudaStream_t st) {
+  if (A.n_units == 0) return EDIS_OK;
+  const size_t smem = static_cast<size_t>(8) * slot_bytes_per_warp + 8 * 32 * sizeof(uint64_t);
+  EDIS_CUDA(cudaFuncSetAttribute(reinterpret_cast<const void*>(kernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(smem)));
+  int blocks = launch_grid(reinterpret_cast<const void*>(kernel), 256, smem, g->sm_count);
+  const int64_t need = (A.n_units + 7) / 8;
+  if (need < blocks) blocks = static_cast<int>(need);
+  kernel<<<blocks, 256, smem, st>>>(A);
+  EDIS_CUDA(cudaGetLastError());
+  return EDIS_OK;
+}
+
 template <class T, int ATT, int RX, int U>
 static int launch_pass(Pass pass, const edis_graph* g, LayerArgs A, cudaStream_t st) {
   A.G = A.C / T::CPW;
   const Schedule& s = pass == Pass::BwdSrc ? g->src : g->dst;
   A.items = s.items;
+  A.n_edges = g->e;
   A.n_units = s.n_items * A.G;
-  if (pass == Pass::Fwd) return launch_persistent(&k_disga_fwd<T, ATT, RX, U>, g, A, st);
+  if (pass == Pass::Fwd) {
+    if constexpr (ATT == 3 && RX == 0 && T::kRing) {
+      // Q_j | V_j must be one contiguous 2-row block of the projection buffer
+      static const int ring_fwd = env_int("EDIS_RING_FWD", 1);
+      if (ring_fwd && ring_ok<T>(A) && A.ldq == A.ldv && A.V == A.Q + A.C * A.D)
+        return launch_ring(&k_disga_fwd_ring<T, EDIS_NS_FWD>, EDIS_NS_FWD * 2 * T::R * 128, g, A, st);
+    }
+    return launch_persistent(&k_disga_fwd<T, ATT, RX, U>, g, A, st);
+  }
   if (pass == Pass::BwdDst) {
+    if constexpr (ATT == 3 && RX == 0 && T::kRing) {
+      static const int ring_dst = env_int("EDIS_RING_DST", 1);
+      if (ring_dst && ring_ok<T>(A))
+        return launch_ring(&k_disga_bwd_dst_ring<T, EDIS_NS_DST>, EDIS_NS_DST * T::R * 128, g, A, st);
+    }
     constexpr int UB = (ATT == 3 && RX == 0 && T::kVec && T::KV == 4) ? EDIS_UB_KV4 : U;
     return launch_persistent(&k_disga_bwd_dst<T, ATT, RX, UB>, g, A, st);
   }
   constexpr int US = (T::kVec && T::KV == 4) ? EDIS_USRC_KV4 : U;
+  if constexpr (ATT == 3 && RX == 0 && T::kRing) {
+    static const int ring_src = env_int("EDIS_RING_SRC", 1);
+    if (ring_src && ring_ok<T>(A)) {
+      constexpr int slot = T::R * 128 + 2 * T::CPW * 4 + 32 * ((T::R + 7) / 8);
+      return launch_ring(&k_disga_bwd_src_ring<T, EDIS_NS_SRC>, EDIS_NS_SRC * slot, g, A, st);
+    }
+  }
   if (RX == 0) return launch_persistent(&k_disga_bwd_src<T, ATT, 1, US>, g, A, st);
   if (RX < 0) {
     if (A.gV) return launch_persistent(&k_disga_bwd_src<T, ATT, 2, US>, g, A, st);

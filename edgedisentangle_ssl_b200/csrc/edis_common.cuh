@@ -96,7 +96,22 @@ __device__ __forceinline__ float rcp_fast(float x) {
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ float sigmoid_mufu(float e) { return rcp_fast(1.0f + ex2_fast(-1.4426950408889634f * e)); }
+// s = sigmoid(e) and sp = s (1 - s) from u = exp(-|e|) in (0, 1]:  s = 1 / (1 + u) (e >= 0) or u / (1 + u),
+// sp = u / (1 + u)^2.  The derivative never goes through "1 - s": with s rounded to fp32 that difference
+// loses log2(1 / (1 - s)) bits, i.e. 1e-5 .. 1e-3 relative for logits of 3 .. 8 (chameleon's features reach
+// |x| ~ 892, so such logits are common there), which showed up as 5e-5 on a score-weight gradient.
+__device__ __forceinline__ void sigmoid_pair(float e, float& s, float& sp) {
+  const float u = ex2_fast(-1.4426950408889634f * fabsf(e));
+  const float r = rcp_fast(1.0f + u);
+  const float ur = u * r;
+  s = e >= 0.0f ? r : ur;
+  sp = ur * r;
+}
+__device__ __forceinline__ float sigmoid_mufu(float e) {
+  float s, sp;
+  sigmoid_pair(e, s, sp);
+  return s;
+}
 __device__ __forceinline__ float exp_mufu(float s) { return ex2_fast(1.4426950408889634f * s); }
 __device__ __forceinline__ float lrelu01(float z) { return fmaxf(z, 0.01f * z); }
 
@@ -200,6 +215,37 @@ __device__ __forceinline__ float sign_pos_f(unsigned mask, int r) {
   static_assert(R <= 24, "sign record wider than the float-one trick supports");
   const int b = R - 1 - r;
   return __uint_as_float((mask & (1u << b)) * (0x3f800000u >> b));
+}
+
+// ---- asynchronous bulk staging (1-D TMA): global -> shared::cta, completion on an mbarrier --------
+// SASS: UBLKCP.S.G + SYNCS.ARRIVE.TRANS64 / SYNCS.PHASECHK (B200_PROFILING.md).  One elected lane issues
+// a whole gathered row (2-4 KB) with ONE instruction; the consumers read it with LDS.128 -- no per-lane
+// 64-bit address chains, no registers held across the DRAM latency.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// blocks (hardware sleep, not a spin on the LSU) until the phase with the given parity has completed
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "EDIS_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra EDIS_DONE;\n"
+      "bra EDIS_WAIT;\n"
+      "EDIS_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
+// bytes: multiple of 16; dst / src 16-byte aligned.  HOT: keep the source lines in L2 (hub rows).
+template <bool HOT>
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(HOT ? kPolEvictLast : kPolEvictFirst) : "memory");
 }
 
 int launch_grid(const void* kernel, int block, size_t smem, int sm_count);

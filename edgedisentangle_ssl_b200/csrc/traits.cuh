@@ -18,6 +18,7 @@ struct VecT {
   static constexpr int CPK = 32 / LPC;
   static constexpr int CPW = KV * CPK;
   static constexpr bool kVec = true;
+  static constexpr bool kRing = LPC_ == 16;   // D == 64 layouts: the bulk-copy (ring) kernels exist for these
   __device__ static __forceinline__ int ch(int k, int lane) { return k * CPK + lane / LPC; }
   __device__ static __forceinline__ bool writer(int lane) { return (lane % LPC) == 0; }
   // value of channel `cc` (0..CPW) held by that channel's lanes -> every lane of the warp
@@ -100,6 +101,7 @@ template <int ND_>
 struct ScaT {
   static constexpr int NCH = 1, RPC = ND_, R = ND_, CPW = 1, KV = 0, LPCV = 1;
   static constexpr bool kVec = false;
+  static constexpr bool kRing = false;
   __device__ static __forceinline__ int ch(int, int) { return 0; }
   __device__ static __forceinline__ bool writer(int lane) { return lane == 0; }
   __device__ static __forceinline__ float bcast(const float (&v)[NCH], int) { return v[0]; }

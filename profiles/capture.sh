@@ -4,9 +4,9 @@
 #   <tag>_launches_full.csv     every launch of that command with its device time (cold, serialised)
 #   <tag>_dram_full.csv         DRAM bytes + time of the layer kernels at full size
 #   <tag>_med_set_full.ncu-rep  --set full (+ source) of one step's six layer-kernel launches, N=400k graph
-tag=${1:-r1c}
-FULL="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-epoch-metric --graph-cache /tmp/graph_A.npy"
-MED="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-epoch-metric --nodes 400000 --raw-edges 5000000 --graph-cache /tmp/graph_M.npy"
+tag=${1:-r2a}
+FULL="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-epoch-metric --no-ssl-metric"
+MED="python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-epoch-metric --no-ssl-metric --nodes 400000 --raw-edges 5000000"
 $FULL > gpurun_out/${tag}_plain_full.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/${tag}_launches_full.csv $FULL > gpurun_out/${tag}_ncu_a.log 2>&1
 $FULL > /dev/null 2>&1 &&

@@ -65,6 +65,21 @@ int main() {
       }
       printf("  %-34s %s: %7.2f ms  %6.1f TFLOP/s  max|diff vs native|/max = %.2e\n", s.name, names[v], ms,
              2.0 * s.M * s.N * s.K / ms / 1e9, mx > 0 ? err / mx : 0.0);
+      if (s.ta && v < 2) {
+        // long-K weight gradient: 16 output entries against a float64 evaluation on the host
+        std::vector<float> ha(na), hb((size_t)s.K * 16);
+        CK(cudaMemcpy(ha.data(), A, na * 4, cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy2D(hb.data(), 16 * 4, B, (size_t)s.N * 4, 16 * 4, s.K, cudaMemcpyDeviceToHost));
+        std::vector<float> hc(16);
+        CK(cudaMemcpy(hc.data(), out, 16 * 4, cudaMemcpyDeviceToHost));      // row 0 of C, first 16 columns
+        double worst = 0, scale = 0;
+        for (int j = 0; j < 16; ++j) {
+          double acc = 0, sa = 0;
+          for (int k = 0; k < s.K; ++k) { acc += (double)ha[(size_t)k * s.M] * hb[(size_t)k * 16 + j]; sa += fabs((double)ha[(size_t)k * s.M] * hb[(size_t)k * 16 + j]); }
+          worst = fmax(worst, fabs(acc - hc[j])); scale = fmax(scale, sa);
+        }
+        printf("      vs float64 (16 entries of row 0): max|err| / sum|terms| = %.2e\n", worst / scale);
+      }
     }
     cudaFree(A); cudaFree(B); cudaFree(C); cudaFree(C2);
   }
