@@ -84,7 +84,8 @@ def workload_config(a, world, e_full=None, extra=None):
     else:
         shape = "ONE graph N=%d, raw draws=%d%s" % (
             a.nodes, a.raw_edges, "" if world == 1 else ", destination rows range-partitioned over %d ranks (strong "
-            "scaling, no planted locality)" % world)
+            "scaling, no planted locality%s)" % (world, "; generated block-wise per rank with uniform mixing between "
+                                                 "the rank ranges" if a.config == "B" else ""))
     cfg = {"workload": "synthetic power-law graph, %s: %s, F=%d, C=%d, D=%d, att=%d, gnn_type=%s, full-batch "
                        "DISGAT.get_em fwd+bwd, train mode dropout=%g" % (name, shape, a.feat, a.nhead, a.nhid, a.att,
                                                                          a.gnn_type, a.dropout),
@@ -359,7 +360,8 @@ def main():
     dev = torch.device("cuda", local)
     par = part = None
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=600))
         from edgedisentangle_ssl_b200 import parallel as par
 
     def barrier():
@@ -382,6 +384,18 @@ def main():
                 graph.save(gpath, _gen_key(a))
             del idx
         n_local, n_total, e_local, lo = a.nodes, a.nodes, graph.e, 0
+    elif strong and a.config == "B":
+        # config[4] (10M nodes / 500M edges) does not fit one host process per rank as ONE generated edge
+        # list; every rank generates only the blocks of the global graph its rows touch (same seeds on both
+        # ends of a block), with UNIFORM mixing between the rank ranges: locality = 1 / world, i.e. no planted
+        # locality -- a node's neighbours are spread over all ranks
+        # (the block generator counts an in-range draw as two directed edges and a cross-range draw as one per
+        # rank: uniform mixing with 2 * raw + N directed edges in total <=> these two arguments)
+        n_total = a.nodes
+        part = par.build_partitioned_power_law(n_total, a.raw_edges * (2 * world - 1) // world, seed=0, rank=rank,
+                                                world=world, device=dev, locality=1.0 / (2 * world - 1),
+                                                max_chunk=a.max_chunk)
+        graph, n_local, e_local, lo = part.graph, part.n_local, part.graph.e, part.lo
     elif strong:
         n_total = a.nodes
         idx, cache_hit = global_graph_indices(a, rank, world, barrier)

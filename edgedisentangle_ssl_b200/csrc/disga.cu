@@ -831,10 +831,10 @@ __global__ void __launch_bounds__(256) k_sage_bwd_src_x(const LayerArgs A) {
 //     registers held across the DRAM latency, and NS rows per warp in flight independent of the
 //     consumer's progress.
 #ifndef EDIS_ROW_COST
-#define EDIS_ROW_COST 6
+#define EDIS_ROW_COST 2
 #endif
 #ifndef EDIS_RPW
-#define EDIS_RPW 4
+#define EDIS_RPW 2
 #endif
 constexpr int kRowCost = EDIS_ROW_COST;   // cost of one work item in units of edges (row prologue / epilogue)
 constexpr int kRangesPerWarp = EDIS_RPW;  // contiguous runs per warp (tail balance vs pipeline restarts)
@@ -890,26 +890,34 @@ struct Ring {
   }
 };
 
-// Neighbour ids of the 32-edge blocks the consumer (block b0) and the producer (b0 or b0 + 1) are in.
+// Neighbour ids of the 32-edge blocks the consumer (block b0) and the producer (b0 or b0 + 1) are in, plus
+// block b0 + 2 already in flight: the load of a block is issued a whole block (32 edges) before the
+// producer first needs it.  (With only two blocks the first `at()` after a block crossing waited a full
+// DRAM latency on the index load: 23 % of the destination pass's stall samples, profiles/r2a.)
+// (edge indices fit int32: edis_graph_create rejects e >= 2^31 - 64)
 struct NbrWindow {
-  int64_t b0;
-  int j0, j1;
-  __device__ __forceinline__ void load(const int32_t* nbr, int64_t n_edges, int64_t e, int lane) {
-    b0 = e >> 5;
-    const int64_t i0 = (b0 << 5) + lane, i1 = i0 + 32;
-    j0 = i0 < n_edges ? __ldg(nbr + i0) : 0;
-    j1 = i1 < n_edges ? __ldg(nbr + i1) : 0;
+  int b0;
+  int j0, j1, j2;
+  __device__ __forceinline__ int ld(const int32_t* nbr, int n_edges, int i) const {
+    return i < n_edges ? __ldg(nbr + i) : 0;
   }
-  __device__ __forceinline__ void advance_to(const int32_t* nbr, int64_t n_edges, int64_t e, int lane) {
+  __device__ __forceinline__ void load(const int32_t* nbr, int n_edges, int e, int lane) {
+    b0 = e >> 5;
+    const int i0 = (b0 << 5) + lane;
+    j0 = ld(nbr, n_edges, i0);
+    j1 = ld(nbr, n_edges, i0 + 32);
+    j2 = ld(nbr, n_edges, i0 + 64);
+  }
+  __device__ __forceinline__ void advance_to(const int32_t* nbr, int n_edges, int e, int lane) {
     if ((e >> 5) != b0) {
       b0 = e >> 5;
       j0 = j1;
-      const int64_t i1 = (b0 << 5) + 32 + lane;
-      j1 = i1 < n_edges ? __ldg(nbr + i1) : 0;
+      j1 = j2;
+      j2 = ld(nbr, n_edges, (b0 << 5) + 64 + lane);
     }
   }
-  __device__ __forceinline__ int at(int64_t e) const {      // e in block b0 or b0 + 1; all lanes
-    return __shfl_sync(FULL, (e >> 5) == b0 ? j0 : j1, static_cast<int>(e & 31));
+  __device__ __forceinline__ int at(int e) const {      // e in block b0 or b0 + 1; all lanes
+    return __shfl_sync(FULL, (e >> 5) == b0 ? j0 : j1, e & 31);
   }
 };
 
@@ -936,10 +944,11 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
     const WarpRange wr = warp_range(A, rg, n_ranges);
     if (wr.i0 >= wr.i1) continue;
     touched = true;
-    const int64_t e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    const int e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    const int n_edges = static_cast<int>(A.n_edges);
     NbrWindow nw;
-    nw.load(A.nbr, A.n_edges, e0, lane);
-    int64_t pe = e0;
+    nw.load(A.nbr, n_edges, e0, lane);
+    int pe = e0;
     auto issue = [&]() {      // all lanes; lane 0 issues the copy of edge pe's source row
       const int raw = nw.at(pe);
       if (lane == 0) {
@@ -954,15 +963,15 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
       ++pe;
     };
     for (int q = 0; q < NS && pe < e1; ++q) issue();
-    int64_t e = e0;
+    int e = e0;
     unsigned sg_n = 0u;
     float ev_n = 0.0f, gx_n = 0.0f;
-    auto load_edge = [&](int64_t ee) {
-      const int64_t so = (ee * 32 + lane) * SBPL;
+    auto load_edge = [&](int ee) {
+      const int64_t so = (static_cast<int64_t>(ee) * 32 + lane) * SBPL;
       sg_n = SBPL == 1 ? static_cast<unsigned>(ld_stream(A.esign + so))
                        : static_cast<unsigned>(ld_stream(reinterpret_cast<const unsigned short*>(A.esign + so)));
-      ev_n = ld_stream(A.edge_e + ee * A.C + myc);
-      gx_n = A.g_edge_e ? ld_stream(A.g_edge_e + ee * A.C + myc) : 0.0f;
+      ev_n = ld_stream(A.edge_e + static_cast<int64_t>(ee) * A.C + myc);
+      gx_n = A.g_edge_e ? ld_stream(A.g_edge_e + static_cast<int64_t>(ee) * A.C + myc) : 0.0f;
     };
     if (e0 < e1) load_edge(e0);
     for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
@@ -974,8 +983,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
       // the next item's row data (g_out, hpre: 2 x ROWB bytes, consecutive rows) into L2 while this row runs
       if (item_id + 1 < wr.i1) {
         const int64_t nrow = static_cast<int64_t>(__ldg(&A.items[item_id + 1].row)) * CD;
-        if (lane < R) prefetch_l2_line<false>(A.g_out + nrow + lane * 32);
-        else if (lane < 2 * R) prefetch_l2_line<false>(A.hpre + nrow + (lane - R) * 32);
+        if (lane < R) {
+          prefetch_l2_line<false>(A.g_out + nrow + lane * 32);
+          prefetch_l2_line<false>(A.P + static_cast<int64_t>(__ldg(&A.items[item_id + 1].row)) * A.ldp + lane * 32);
+        } else if (lane < 2 * R) {
+          prefetch_l2_line<false>(A.hpre + nrow + (lane - R) * 32);
+        }
       }
       float dh[R], tc;
       const float wsum = __ldg(A.stats + srow * 2 * A.C + myc);
@@ -1001,7 +1014,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
 #pragma unroll
       for (int k = 0; k < NCH; ++k) dsum[k] = 0.0f;
       for (; e < it.end; ++e) {
-        nw.advance_to(A.nbr, A.n_edges, e, lane);
+        nw.advance_to(A.nbr, n_edges, e, lane);
         // per-edge streams (coalesced, sequential in e): sign record, logit, upstream logit gradient --
         // loaded ONE EDGE AHEAD into registers so that their latency hides under this edge's math
         const unsigned sg = sg_n;
@@ -1024,12 +1037,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
         float s, sgrad;
         sigmoid_pair(ev, s, sgrad);
         const float alpha = exp_mufu(s) * inv;
-        const float ms = A.training ? keep_scale(A.seed, e * A.C + myc, A.p, A.inv_keep) : 1.0f;
+        const float ms = A.training ? keep_scale(A.seed, static_cast<int64_t>(e) * A.C + myc, A.p, A.inv_keep) : 1.0f;
         const float ds = alpha * (gdot * ms - tc);
         const float de = fmaf(ds, sgrad, gx);
         if (T::own_writer(lane)) {
-          st_stream(A.edge_rec + e * 2 * A.C + myc, alpha * ms);
-          st_stream(A.edge_rec + e * 2 * A.C + A.C + myc, de);
+          st_stream(A.edge_rec + static_cast<int64_t>(e) * 2 * A.C + myc, alpha * ms);
+          st_stream(A.edge_rec + static_cast<int64_t>(e) * 2 * A.C + A.C + myc, de);
         }
 #pragma unroll
         for (int k = 0; k < NCH; ++k) {
@@ -1093,11 +1106,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src_ring(const Lay
     const WarpRange wr = warp_range(A, rg, n_ranges);
     if (wr.i0 >= wr.i1) continue;
     touched = true;
-    const int64_t e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    const int e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    const int n_edges = static_cast<int>(A.n_edges);
     NbrWindow nw, ew;
-    nw.load(A.nbr, A.n_edges, e0, lane);
-    ew.load(A.eid, A.n_edges, e0, lane);
-    int64_t pe = e0;
+    nw.load(A.nbr, n_edges, e0, lane);
+    ew.load(A.eid, n_edges, e0, lane);
+    int pe = e0;
     auto issue = [&]() {
       const int raw = nw.at(pe);
       const int64_t edge = ew.at(pe);
@@ -1116,7 +1130,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src_ring(const Lay
       ++pe;
     };
     for (int q = 0; q < NS && pe < e1; ++q) issue();
-    int64_t e = e0;
+    int e = e0;
     for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
       const Item it = A.items[item_id];
       if (item_id + 1 < wr.i1 && lane < R)      // next source row's Q_j (row epilogue operand) into L2
@@ -1127,8 +1141,8 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src_ring(const Lay
 #pragma unroll
       for (int k = 0; k < NCH; ++k) dss[k] = 0.0f;
       for (; e < it.end; ++e) {
-        nw.advance_to(A.nbr, A.n_edges, e, lane);
-        ew.advance_to(A.eid, A.n_edges, e, lane);
+        nw.advance_to(A.nbr, n_edges, e, lane);
+        ew.advance_to(A.eid, n_edges, e, lane);
         const unsigned char* sp = ring.wait_next();
         const float* rowp = reinterpret_cast<const float*>(sp);
         const float* recp = reinterpret_cast<const float*>(sp + ROWB);
@@ -1209,10 +1223,11 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
   for (int64_t rg = static_cast<int64_t>(blockIdx.x) * 8 + wid; rg < n_ranges; rg += nwarps) {
     const WarpRange wr = warp_range(A, rg, n_ranges);
     if (wr.i0 >= wr.i1) continue;
-    const int64_t e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    const int e0 = __ldg(&A.items[wr.i0].beg), e1 = __ldg(&A.items[wr.i1 - 1].end);
+    const int n_edges = static_cast<int>(A.n_edges);
     NbrWindow nw;
-    nw.load(A.nbr, A.n_edges, e0, lane);
-    int64_t pe = e0;
+    nw.load(A.nbr, n_edges, e0, lane);
+    int pe = e0;
     auto issue = [&]() {
       const int raw = nw.at(pe);
       if (lane == 0) {
@@ -1227,7 +1242,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
       ++pe;
     };
     for (int q = 0; q < NS && pe < e1; ++q) issue();
-    int64_t e = e0;
+    int e = e0;
     for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
       const Item it = A.items[item_id];
       const int64_t srow = static_cast<int64_t>(it.row);
@@ -1238,7 +1253,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
       float acc[R], ws = 0.0f, wms = 0.0f;
       zero<T>(acc);
       for (; e < it.end; ++e) {
-        nw.advance_to(A.nbr, A.n_edges, e, lane);
+        nw.advance_to(A.nbr, n_edges, e, lane);
         const float* sp = reinterpret_cast<const float*>(ring.wait_next());
         float q[R], h[R];
 #pragma unroll
@@ -1262,12 +1277,12 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
         // h is still only in registers of this lane: the slot is free once all lanes have loaded it
         if (pe < e1) issue();
         if (A.esign) {
-          const int64_t so = (e * 32 + lane) * SBPL;
+          const int64_t so = (static_cast<int64_t>(e) * 32 + lane) * SBPL;
           if (SBPL == 1) st_stream(A.esign + so, static_cast<unsigned char>(mask));
           else st_stream(reinterpret_cast<unsigned short*>(A.esign + so), static_cast<unsigned short>(mask));
         }
         const float w = exp_mufu(sigmoid_mufu(ev));
-        const float ms = A.training ? keep_scale(A.seed, e * A.C + myc, A.p, A.inv_keep) : 1.0f;
+        const float ms = A.training ? keep_scale(A.seed, static_cast<int64_t>(e) * A.C + myc, A.p, A.inv_keep) : 1.0f;
         const float wm = w * ms;
         ws += w;
         wms += wm;
@@ -1277,7 +1292,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
 #pragma unroll
           for (int r = k * RPC; r < (k + 1) * RPC; ++r) acc[r] = fmaf(wk, h[r], acc[r]);
         }
-        if (T::own_writer(lane)) st_stream(A.edge_e + e * A.C + myc, ev);
+        if (T::own_writer(lane)) st_stream(A.edge_e + static_cast<int64_t>(e) * A.C + myc, ev);
       }
       if (it.slot < 0) {
         float o[R], hp[R], br[R];

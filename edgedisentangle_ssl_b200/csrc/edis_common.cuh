@@ -86,15 +86,27 @@ __device__ __forceinline__ float sigmoidf_fast(float x) {
 // Layer kernels: sigmoid and exp(sigmoid) straight on the MUFU units (ex2.approx / rcp.approx with
 // flush-to-zero, no range fix-ups: 2^-22 relative).  Forward and backward use the SAME functions, so
 // the softmax weights recomputed in the backward are bit-identical to the forward's row sums.
+// EDIS_EXACT_MATH=1 (build-time, diagnostics): libm-accurate exp2 / division instead of the MUFU approximations
+#ifndef EDIS_EXACT_MATH
+#define EDIS_EXACT_MATH 0
+#endif
 __device__ __forceinline__ float ex2_fast(float x) {
+#if EDIS_EXACT_MATH
+  return exp2f(x);
+#else
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 __device__ __forceinline__ float rcp_fast(float x) {
+#if EDIS_EXACT_MATH
+  return __frcp_rn(x);
+#else
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#endif
 }
 // s = sigmoid(e) and sp = s (1 - s) from u = exp(-|e|) in (0, 1]:  s = 1 / (1 + u) (e >= 0) or u / (1 + u),
 // sp = u / (1 + u)^2.  The derivative never goes through "1 - s": with s rounded to fp32 that difference

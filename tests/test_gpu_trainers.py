@@ -133,7 +133,12 @@ def test_train_steps_vs_reference_golden(tag):
         sens = kink_sensitivity(lambda: arbiter(nm, snap), f64, floor64)     # helpers.rounding_noise: why
         for name, prm in enc.named_parameters():
             if name in f64:
-                tol = max(2e-5, 2.0 * sens[name])
+                # 1e-4, not 2e-5: the kernels take the softmax backward's row term t_i = sum_k alpha_ik dalpha_ik
+                # from the stored aggregate (<gh_i, agg_i>, single pass) -- on the near-constant layer-2
+                # messages of these toy graphs that form carries ~6e-5 on the tiny `a` gradients (1e-3 of the
+                # step's largest) in PLAIN fp32 torch as well, against 5e-6 for the reference's two-reduction
+                # form (tests/test_oracle_golden.py::test_single_pass_softmax_backward_conditioning)
+                tol = max(1e-4 if name.endswith(".a") else 2e-5, 2.0 * sens[name])
                 if nm == "cls" and name in refs:
                     tol = max(tol, 16.0 * rel_err(refs[name], f64[name], floor64))
                 err = rel_err(prm.grad.cpu(), f64[name], floor64)
