@@ -922,7 +922,7 @@ struct NbrWindow {
 };
 
 // backward, destination pass (att 3, per-channel operand, whole-row warps): ring of V_j rows
-template <class T, int NS>
+template <class T, int NS, bool TRAIN, bool GX>
 __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const LayerArgs A) {
   constexpr int R = T::R, NCH = T::NCH, RPC = T::RPC;
   constexpr int ROWB = R * 128;         // C * D * 4 bytes with C == T::CPW
@@ -949,29 +949,30 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
     NbrWindow nw;
     nw.load(A.nbr, n_edges, e0, lane);
     int pe = e0;
-    auto issue = [&]() {      // all lanes; lane 0 issues the copy of edge pe's source row
-      const int raw = nw.at(pe);
-      if (lane == 0) {
+    // all lanes; lane 0 issues the copy of edge pe's source row when pe < e1 (ONE predicate: the index is
+    // clamped so that the shuffle is unconditional)
+    auto issue = [&]() {
+      const int raw = nw.at(min(pe, e1 - 1));
+      if (lane == 0 && pe < e1) {
         const uint32_t s = ring.kp % NS;
         const uint32_t bar = ring.bar0 + 8 * s;
-        const float* src = A.V + static_cast<int64_t>(raw & kIdMask) * A.ldv;
         mbar_expect_tx(bar, ROWB);
-        if (is_hot(raw, A.hot_min)) bulk_g2s<true>(ring.slot0 + s * ROWB, src, ROWB, bar);
-        else bulk_g2s<false>(ring.slot0 + s * ROWB, src, ROWB, bar);
+        bulk_g2s_pol(ring.slot0 + s * ROWB, A.V + static_cast<int64_t>(raw & kIdMask) * A.ldv, ROWB, bar,
+                     l2_policy(raw, A.hot_min));
       }
-      ++ring.kp;
+      ring.kp += pe < e1 ? 1u : 0u;
       ++pe;
     };
-    for (int q = 0; q < NS && pe < e1; ++q) issue();
+    for (int q = 0; q < NS; ++q) issue();      // (a run of edge-less rows has e0 == e1: nothing is issued)
     int e = e0;
     unsigned sg_n = 0u;
     float ev_n = 0.0f, gx_n = 0.0f;
-    auto load_edge = [&](int ee) {
+    auto load_edge = [&](int ee) {      // ee clamped by the caller: no branch
       const int64_t so = (static_cast<int64_t>(ee) * 32 + lane) * SBPL;
       sg_n = SBPL == 1 ? static_cast<unsigned>(ld_stream(A.esign + so))
                        : static_cast<unsigned>(ld_stream(reinterpret_cast<const unsigned short*>(A.esign + so)));
       ev_n = ld_stream(A.edge_e + static_cast<int64_t>(ee) * A.C + myc);
-      gx_n = A.g_edge_e ? ld_stream(A.g_edge_e + static_cast<int64_t>(ee) * A.C + myc) : 0.0f;
+      if (GX) gx_n = ld_stream(A.g_edge_e + static_cast<int64_t>(ee) * A.C + myc);
     };
     if (e0 < e1) load_edge(e0);
     for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
@@ -1019,7 +1020,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
         // loaded ONE EDGE AHEAD into registers so that their latency hides under this edge's math
         const unsigned sg = sg_n;
         const float ev = ev_n, gx = gx_n;
-        if (e + 1 < e1) load_edge(e + 1);
+        load_edge(min(e + 1, e1 - 1));
         const float* sp = reinterpret_cast<const float*>(ring.wait_next());
         float h[R];
 #pragma unroll
@@ -1033,11 +1034,11 @@ __global__ void __launch_bounds__(256, EDIS_MINB_DST) k_disga_bwd_dst_ring(const
 #pragma unroll
         for (int r = 0; r < R; ++r) gpart[r / RPC] = fmaf(dh[r], h[r], gpart[r / RPC]);
         const float gdot = T::reduce_own(gpart, lane);     // shuffles: every lane has consumed its slot reads
-        if (pe < e1) issue();                              // refill the slot just read
+        issue();                                           // refill the slot just read
         float s, sgrad;
         sigmoid_pair(ev, s, sgrad);
         const float alpha = exp_mufu(s) * inv;
-        const float ms = A.training ? keep_scale(A.seed, static_cast<int64_t>(e) * A.C + myc, A.p, A.inv_keep) : 1.0f;
+        const float ms = TRAIN ? keep_scale(A.seed, static_cast<int64_t>(e) * A.C + myc, A.p, A.inv_keep) : 1.0f;
         const float ds = alpha * (gdot * ms - tc);
         const float de = fmaf(ds, sgrad, gx);
         if (T::own_writer(lane)) {
@@ -1113,23 +1114,22 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src_ring(const Lay
     ew.load(A.eid, n_edges, e0, lane);
     int pe = e0;
     auto issue = [&]() {
-      const int raw = nw.at(pe);
-      const int64_t edge = ew.at(pe);
-      if (lane == 0) {
+      const int pc = min(pe, e1 - 1);
+      const int raw = nw.at(pc);
+      const int64_t edge = ew.at(pc);
+      if (lane == 0 && pe < e1) {
         const uint32_t s = ring.kp % NS;
         const uint32_t bar = ring.bar0 + 8 * s;
         const uint32_t dst = ring.slot0 + s * SLOTB;
-        const float* src = A.gh + static_cast<int64_t>(raw & kIdMask) * CD;
         mbar_expect_tx(bar, SLOTB);
-        if (is_hot(raw, A.hot_min)) bulk_g2s<true>(dst, src, ROWB, bar);
-        else bulk_g2s<false>(dst, src, ROWB, bar);
+        bulk_g2s_pol(dst, A.gh + static_cast<int64_t>(raw & kIdMask) * CD, ROWB, bar, l2_policy(raw, A.hot_min));
         bulk_g2s<false>(dst + ROWB, A.edge_rec + edge * 2 * A.C, RECB, bar);
         bulk_g2s<false>(dst + ROWB + RECB, A.esign + edge * SIGNB, SIGNB, bar);
       }
-      ++ring.kp;
+      ring.kp += pe < e1 ? 1u : 0u;
       ++pe;
     };
-    for (int q = 0; q < NS && pe < e1; ++q) issue();
+    for (int q = 0; q < NS; ++q) issue();      // (a run of edge-less rows has e0 == e1: nothing is issued)
     int e = e0;
     for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
       const Item it = A.items[item_id];
@@ -1169,7 +1169,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_bwd_src_ring(const Lay
           dss[k] += de[k];
         }
         __syncwarp();                 // every lane has read the slot
-        if (pe < e1) issue();
+        issue();
       }
       const int64_t jrow = static_cast<int64_t>(it.row);
       if (it.end > it.beg) {
@@ -1229,19 +1229,18 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
     nw.load(A.nbr, n_edges, e0, lane);
     int pe = e0;
     auto issue = [&]() {
-      const int raw = nw.at(pe);
-      if (lane == 0) {
+      const int raw = nw.at(min(pe, e1 - 1));
+      if (lane == 0 && pe < e1) {
         const uint32_t s = ring.kp % NS;
         const uint32_t bar = ring.bar0 + 8 * s;
-        const float* src = A.Q + static_cast<int64_t>(raw & kIdMask) * A.ldq;      // Q_j | V_j adjacent
         mbar_expect_tx(bar, SLOTB);
-        if (is_hot(raw, A.hot_min)) bulk_g2s<true>(ring.slot0 + s * SLOTB, src, SLOTB, bar);
-        else bulk_g2s<false>(ring.slot0 + s * SLOTB, src, SLOTB, bar);
+        bulk_g2s_pol(ring.slot0 + s * SLOTB, A.Q + static_cast<int64_t>(raw & kIdMask) * A.ldq, SLOTB, bar,
+                     l2_policy(raw, A.hot_min));                                      // Q_j | V_j adjacent
       }
-      ++ring.kp;
+      ring.kp += pe < e1 ? 1u : 0u;
       ++pe;
     };
-    for (int q = 0; q < NS && pe < e1; ++q) issue();
+    for (int q = 0; q < NS; ++q) issue();      // (a run of edge-less rows has e0 == e1: nothing is issued)
     int e = e0;
     for (int64_t item_id = wr.i0; item_id < wr.i1; ++item_id) {
       const Item it = A.items[item_id];
@@ -1275,7 +1274,7 @@ __global__ void __launch_bounds__(256, EDIS_MINB) k_disga_fwd_ring(const LayerAr
         }
         const float ev = T::reduce_own(part, lane);      // shuffles: q has been consumed by every lane
         // h is still only in registers of this lane: the slot is free once all lanes have loaded it
-        if (pe < e1) issue();
+        issue();
         if (A.esign) {
           const int64_t so = (static_cast<int64_t>(e) * 32 + lane) * SBPL;
           if (SBPL == 1) st_stream(A.esign + so, static_cast<unsigned char>(mask));
@@ -1377,8 +1376,15 @@ static int launch_pass(Pass pass, const edis_graph* g, LayerArgs A, cudaStream_t
   if (pass == Pass::BwdDst) {
     if constexpr (ATT == 3 && RX == 0 && T::kRing) {
       static const int ring_dst = env_int("EDIS_RING_DST", 1);
-      if (ring_dst && ring_ok<T>(A))
-        return launch_ring(&k_disga_bwd_dst_ring<T, EDIS_NS_DST>, EDIS_NS_DST * T::R * 128, g, A, st);
+      if (ring_dst && ring_ok<T>(A)) {
+        constexpr int sb = EDIS_NS_DST * T::R * 128;
+        if (A.training) {
+          if (A.g_edge_e) return launch_ring(&k_disga_bwd_dst_ring<T, EDIS_NS_DST, true, true>, sb, g, A, st);
+          return launch_ring(&k_disga_bwd_dst_ring<T, EDIS_NS_DST, true, false>, sb, g, A, st);
+        }
+        if (A.g_edge_e) return launch_ring(&k_disga_bwd_dst_ring<T, EDIS_NS_DST, false, true>, sb, g, A, st);
+        return launch_ring(&k_disga_bwd_dst_ring<T, EDIS_NS_DST, false, false>, sb, g, A, st);
+      }
     }
     constexpr int UB = (ATT == 3 && RX == 0 && T::kVec && T::KV == 4) ? EDIS_UB_KV4 : U;
     return launch_persistent(&k_disga_bwd_dst<T, ATT, RX, UB>, g, A, st);

@@ -260,6 +260,14 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(HOT ? kPolEvictLast : kPolEvictFirst) : "memory");
 }
 
+// same with the L2 policy in a register (issued by one lane, so the uniform-datapath move costs nothing extra
+// and the hot / cold choice needs no branch)
+__device__ __forceinline__ void bulk_g2s_pol(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar), "l"(policy) : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy(int raw, int hot_min) { return is_hot(raw, hot_min) ? kPolEvictLast : kPolEvictFirst; }
+
 int launch_grid(const void* kernel, int block, size_t smem, int sm_count);
 
 }  // namespace edis
