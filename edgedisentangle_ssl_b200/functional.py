@@ -593,6 +593,12 @@ class SslWmse(torch.autograd.Function):
         target = target.contiguous()
         m, cs = scores.shape
         m_total = m if m_total is None else int(m_total)
+        ctx.n_pos, ctx.m_total = int(n_pos), m_total
+        if m == 0:
+            # a rank whose slice of a partitioned pair set is empty contributes 0 (and must not raise while
+            # its peers sit in the next collective)
+            ctx.save_for_backward(scores, target)
+            return scores.new_zeros(())
         loss = torch.empty(1, dtype=torch.float32, device=scores.device)
         ws = torch.empty(8, dtype=torch.uint8, device=scores.device)
         check(lib.edis_ssl_wmse_fwd(m, cs, _ptr(scores), _ptr(target), int(n_pos), m_total, _ptr(loss), _ptr(ws), 8,
@@ -605,6 +611,8 @@ class SslWmse(torch.autograd.Function):
     def backward(ctx, g_loss):
         scores, target = ctx.saved_tensors
         m, cs = scores.shape
+        if m == 0:
+            return torch.zeros_like(scores), None, None, None
         g_scores = torch.empty_like(scores)
         g_loss = g_loss.reshape(1).contiguous().float()
         check(lib.edis_ssl_wmse_bwd(m, cs, _ptr(scores), _ptr(target), ctx.n_pos, ctx.m_total, _ptr(g_loss),

@@ -8,7 +8,6 @@ reference, so a reference `state_dict` loads unchanged and same-seed initialisat
   GraphConvolution layers.py:16-59    (parameters; aggregation is fused upstream)
 All channels of a DISGAT layer run in ONE fused kernel launch (`run_channels`).
 """
-import itertools
 import math
 import os
 
@@ -22,12 +21,23 @@ from .functional import (ChannelLinear, DisGAFused, PairList, PairScore, Proj3xT
                          use_proj3x)
 from .graph import as_graph
 
-_seed_counter = itertools.count(1)
+_seed_state = {"count": 0}
 
 
 def _next_seed():
     # counter-based dropout stream derived from torch's seed: no device->host sync
-    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + next(_seed_counter) * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+    _seed_state["count"] += 1
+    return (torch.initial_seed() * 0x9E3779B97F4A7C15 + _seed_state["count"] * 0xD1B54A32D192ED03) & (2 ** 64 - 1)
+
+
+def dropout_stream_state():
+    """Position of the attention-dropout stream (saved with a checkpoint so that a resumed run does not
+    replay the masks of its first epochs)."""
+    return int(_seed_state["count"])
+
+
+def set_dropout_stream_state(count):
+    _seed_state["count"] = int(count)
 
 
 class GraphConvolution(nn.Module):

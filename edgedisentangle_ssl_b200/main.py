@@ -31,7 +31,9 @@ def save_model(args, encoder, trainers, epoch, root="."):
     state ride along under 'trainers', so a run can be RESUMED, not only warm-started."""
     d, path = checkpoint_path(args, epoch, root)
     os.makedirs(d, exist_ok=True)
-    content = {"encoder": encoder.state_dict(), "epoch": epoch, "trainers": []}
+    from .layers import dropout_stream_state
+    content = {"encoder": encoder.state_dict(), "epoch": epoch, "trainers": [],
+               "dropout_stream": dropout_stream_state()}
     for tr in trainers:
         content["trainers"].append({"class": type(tr).__name__,
                                     "models": [m.state_dict() for m in tr.models[1:]],     # [0] is the encoder
@@ -53,6 +55,9 @@ def load_model(args, encoder, trainers=(), root="."):
             m.load_state_dict(sd)
         for o, sd in zip(tr.models_opt, st["optimizers"]):
             o.load_state_dict(sd)
+    if "dropout_stream" in content:
+        from .layers import set_dropout_stream_state
+        set_dropout_stream_state(content["dropout_stream"])
     print("successfully loaded: {}".format(args.load))
     return content.get("epoch", args.load)
 

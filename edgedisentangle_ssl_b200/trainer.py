@@ -287,13 +287,16 @@ class _PairTrainer(Trainer):
         # "exact": the reference's RNG stream replayed bit for bit (O(N^2) uniforms on the host);
         # "device": same distribution in O(M) on the GPU (needed beyond N ~ 5e4; EDIS_SAMPLER=device)
         mode = os.environ.get("EDIS_SAMPLER") or ("exact" if lab.n <= 50_000 else "device")
+        self._n_pos = []          # positives per set, counted where the labels are made: no device sync later
         for k, pos in enumerate(lab.sets):
             if mode == "exact":
                 pairs, y = sample_pairs(lab.n, pos)
+                self._n_pos.append(int(np.count_nonzero(y)))
                 masks.append(torch.from_numpy(pairs).to(dev))
                 labels.append(torch.from_numpy(y).to(dev))
             else:
                 pairs, y = sample_pairs_device(lab.n, lab.keys_on(dev)[k])
+                self._n_pos.append(None)
                 masks.append(pairs)
                 labels.append(y)
         return labels, masks
@@ -308,7 +311,9 @@ class _PairTrainer(Trainer):
         ranges = self._ranges(nsets)
         r = self.models[0].traverse(feature, adj, self.fusers, aux=masks, aux_ranges=ranges,
                                     need_layer2_agg=False)
-        n_pos = [int((y != 0).sum()) for y in labels]
+        known = getattr(self, "_n_pos", None) or [None] * nsets
+        n_pos = [known[k] if k < len(known) and known[k] is not None else int((y != 0).sum())
+                 for k, y in enumerate(labels)]
         loss = None
         for layer, auxs in enumerate(r["aux"]):
             if self.constrain_layer == 0 or self.constrain_layer == layer:
