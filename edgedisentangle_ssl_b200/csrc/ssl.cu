@@ -98,6 +98,10 @@ __global__ void __launch_bounds__(256) k_pair_fwd(const PairArgs A) {
   }
 }
 
+// (A ring / bulk-copy variant of this kernel -- contiguous pair runs per warp, one cp.async.bulk per pair for the
+// channel group's 1 KB slice of Q_j -- was built and measured in round 2: parity-green, but the SupEdge step on
+// config A went from 707 to 724 ms.  With two channel groups per pair the copies are only 1 KB each and the
+// per-copy issue cost is paid twice; removed again.  profiles/README.md.)
 // Backward: gP_i and ga accumulate in registers over runs of equal i (lists are row-sorted);
 // gQ_j (and gP_i at run ends) go out as 128-bit vector reductions.
 template <class T, int ATT>
