@@ -257,7 +257,10 @@ def test_accuracy_parity_within_seed_noise(key, ds, gnn, at, sampler, monkeypatc
     seed-to-seed spread as the band, and every run must be far above chance.  cora / cora_full use the
     label-derived synthetic features of SURVEY 8(d) (their blobs are missing), on which the reference
     itself is unstable after ~epoch 80 (4 of 5 cora seeds collapse to the majority class 0.3024): the
-    comparison is made at epoch 40, where both sides are still in the regime the hot path decides."""
+    comparison is made at epoch 40, where both sides are still in the regime the hot path decides.  On
+    cora_full (70 classes) the reference is at 0.047 = the majority-class share for every seed at epoch 40
+    (49 s per CPU epoch bounded how far the reference curves could be recorded); the B200 path lands on the
+    same 0.047."""
     import contextlib
     import io
     import json
