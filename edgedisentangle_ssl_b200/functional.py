@@ -261,6 +261,60 @@ class DisGAFused(torch.autograd.Function):
                 ga if ctx.has_a else None, gbias, None, None, None)
 
 
+def sage_forward_raw(graph, d, P, ldp, Q, ldq, X, a, want_sign):
+    """One edis_disga_sage_fwd launch on raw score operands (ctypes pointers + row strides) and the shared
+    operand X[n_cols, F] (tensor).  d.Dv / d.flags must be set.  -> (agg[n, C*F], edge_e, stats, esign)."""
+    n, e, Fin, C = graph.n, graph.e, X.shape[1], d.C
+    if X.shape[0] != graph.n_cols:
+        raise _lib.EdisError("X has %d rows, graph has %d source nodes" % (X.shape[0], graph.n_cols))
+    agg = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
+    edge_e = torch.empty(e, C, dtype=torch.float32, device=X.device)
+    stats = torch.empty(n, 2 * C, dtype=torch.float32, device=X.device)
+    ws, nbytes = _workspace(graph, C * Fin + 2 * C, X)
+    esign = _sign_rec(graph, d, X.device, want_sign)
+    plain = bool(d.flags & _lib.FLAG_PLAIN_MEAN)
+    with _timed("disga_sage_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0),
+                kernel_bytes("fwd", n, graph.n_cols, e, d.att, C, d.D, Fin, sage=not plain)):
+        check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X), X.stride(0),
+                                      _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(ws), nbytes,
+                                      _stream()),
+              "edis_disga_sage_fwd")
+    return agg, edge_e, stats, esign
+
+
+def sage_backward_raw(graph, d, P, ldp, Q, ldq, X, a, agg, edge_e, stats, esign, g_agg, g_edge_e, gP, ldgp, gQ, ldgq,
+                      ga, need_gx):
+    """The passes of edis_disga_sage_bwd on raw operands; the caller owns gP / gQ / ga.  -> gX[n_cols, F] or None."""
+    C, D, att, Fin = d.C, d.D, d.att, d.Dv
+    CD = C * D
+    n, e, nc = graph.n, graph.e, graph.n_cols
+    dev = X.device
+    gX = torch.empty(nc, Fin, dtype=torch.float32, device=dev) if need_gx else None
+    edge_rec = _edge_rec(graph, d, dev)
+    gh = torch.empty(n, C * Fin, dtype=torch.float32, device=dev)
+    ws, nbytes = _workspace(graph, 2 * CD + 2 * C + Fin, X)
+    base = d.flags
+    plain = bool(base & _lib.FLAG_PLAIN_MEAN)
+    fused_gx = bool(lib.edis_disga_sage_fused_gx(ctypes.byref(d)))
+    kb = lambda kind: kernel_bytes(kind, n, nc, e, att, C, D, Fin, sage=not plain)
+    phases = [("disga_sage_bwd_dst", _lib.FLAG_PHASE_DST, 1 + (1 if graph.info["dst_slots"] else 0), kb("bwd_dst")),
+              ("disga_sage_bwd_src", _lib.FLAG_PHASE_SRC, 1 + (1 if graph.info["src_slots"] else 0),
+               kb("bwd_src" if (fused_gx and need_gx) else "bwd_src_score"))]
+    if need_gx and not fused_gx:
+        phases.append(("disga_sage_bwd_gx", _lib.FLAG_PHASE_GX, 1 + (1 if graph.info["src_slots"] else 0),
+                       kb("bwd_gx")))
+    for name, bit, nl, nb in phases:
+        d.flags = base | bit
+        with _timed(name, graph, nl, nb):
+            check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X),
+                                          X.stride(0), _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_agg),
+                                          _ptr(g_edge_e), gP, ldgp, gQ, ldgq, _ptr(ga), _ptr(gX),
+                                          _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream()),
+                  "edis_disga_sage_bwd")
+    d.flags = base
+    return gX
+
+
 class SageFused(torch.autograd.Function):
     """Scoring -> softmax -> dropout -> aggregation of the RAW layer input x, shared by all channels.
 
@@ -284,24 +338,11 @@ class SageFused(torch.autograd.Function):
             proj, ld = _rows(proj, "proj")
             P, Q, ldp, ldq = _off(proj, off_p), _off(proj, off_q), ld, ld
         a = a.contiguous() if a is not None else None
-        n, e, Fin = graph.n, graph.e, X.shape[1]
-        if X.shape[0] != graph.n_cols:
-            raise _lib.EdisError("X has %d rows, graph has %d source nodes" % (X.shape[0], graph.n_cols))
-        agg = torch.empty(n, C * Fin, dtype=torch.float32, device=X.device)
-        edge_e = torch.empty(e, C, dtype=torch.float32, device=X.device)
-        stats = torch.empty(n, 2 * C, dtype=torch.float32, device=X.device)
-        ws, nbytes = _workspace(graph, C * Fin + 2 * C, X)
         d = _desc(att, C, D, training, p, seed)
-        d.Dv = Fin
+        d.Dv = X.shape[1]
         d.flags = (_lib.FLAG_PLAIN_MEAN if plain else 0) | (0 if ctx.needs_input_grad[10] else _lib.FLAG_NO_GX)
-        esign = _sign_rec(graph, d, X.device, any(ctx.needs_input_grad))
-        with _timed("disga_sage_fwd", graph, 1 + (1 if graph.info["dst_slots"] else 0),
-                    kernel_bytes("fwd", n, graph.n_cols, e, att, C, D, Fin, sage=not plain)):
-            check(lib.edis_disga_sage_fwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X), ldx,
-                                          _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(ws), nbytes,
-                                          _stream()),
-                  "edis_disga_sage_fwd")
-        ctx.graph, ctx.d, ctx.offs, ctx.ldx, ctx.plain = graph, d, (off_p, off_q), ldx, bool(plain)
+        agg, edge_e, stats, esign = sage_forward_raw(graph, d, P, ldp, Q, ldq, X, a, any(ctx.needs_input_grad))
+        ctx.graph, ctx.d, ctx.offs, ctx.plain = graph, d, (off_p, off_q), bool(plain)
         ctx.has_a = a is not None
         ctx.save_for_backward(proj, sdst, ssrc, a, X, agg, edge_e, stats, esign)
         ctx.set_materialize_grads(False)
@@ -311,9 +352,9 @@ class SageFused(torch.autograd.Function):
     def backward(ctx, g_agg, g_edge_e):
         proj, sdst, ssrc, a, X, agg, edge_e, stats, esign = ctx.saved_tensors
         graph, d = ctx.graph, ctx.d
-        C, D, att, Fin = d.C, d.D, d.att, d.Dv
+        C, D, att = d.C, d.D, d.att
         CD = C * D
-        n, e, nc = graph.n, graph.e, graph.n_cols
+        n, nc = graph.n, graph.n_cols
         rect = nc > n
         off_p, off_q = ctx.offs
         dev = X.device
@@ -341,29 +382,9 @@ class SageFused(torch.autograd.Function):
             else:
                 gQ, ldgq = _off(g_proj, off_q), W
         need_gx = not (d.flags & _lib.FLAG_NO_GX)
-        gX = torch.empty(nc, Fin, dtype=torch.float32, device=dev) if need_gx else None
         ga = torch.zeros(C, D, dtype=torch.float32, device=dev) if att == 3 else None
-        edge_rec = _edge_rec(graph, d, dev)
-        gh = torch.empty(n, C * Fin, dtype=torch.float32, device=dev)
-        ws, nbytes = _workspace(graph, 2 * CD + 2 * C + Fin, X)
-        base = d.flags
-        fused_gx = bool(lib.edis_disga_sage_fused_gx(ctypes.byref(d)))
-        kb = lambda kind: kernel_bytes(kind, n, nc, e, att, C, D, Fin, sage=not ctx.plain)
-        phases = [("disga_sage_bwd_dst", _lib.FLAG_PHASE_DST, 1 + (1 if graph.info["dst_slots"] else 0), kb("bwd_dst")),
-                  ("disga_sage_bwd_src", _lib.FLAG_PHASE_SRC, 1 + (1 if graph.info["src_slots"] else 0),
-                   kb("bwd_src" if (fused_gx and need_gx) else "bwd_src_score"))]
-        if need_gx and not fused_gx:
-            phases.append(("disga_sage_bwd_gx", _lib.FLAG_PHASE_GX, 1 + (1 if graph.info["src_slots"] else 0),
-                           kb("bwd_gx")))
-        for name, bit, nl, nb in phases:
-            d.flags = base | bit
-            with _timed(name, graph, nl, nb):
-                check(lib.edis_disga_sage_bwd(graph.handle, ctypes.byref(d), P, ldp, Q, ldq, _ptr(a), _ptr(X),
-                                              ctx.ldx, _ptr(agg), _ptr(edge_e), _ptr(stats), _ptr(esign), _ptr(g_agg),
-                                              _ptr(g_edge_e), gP, ldgp, gQ, ldgq, _ptr(ga), _ptr(gX),
-                                              _ptr(edge_rec), _ptr(gh), _ptr(ws), nbytes, _stream()),
-                      "edis_disga_sage_bwd")
-        d.flags = base
+        gX = sage_backward_raw(graph, d, P, ldp, Q, ldq, X, a, agg, edge_e, stats, esign, g_agg, g_edge_e, gP, ldgp,
+                               gQ, ldgq, ga, need_gx)
         if gq_sep is not None:
             g_proj[:, off_p:off_p + CD] += gq_sep
         return (None, None, None, None, g_proj, None, None, g_sd, g_ss, ga if ctx.has_a else None, gX,

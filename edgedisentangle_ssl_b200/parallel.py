@@ -318,7 +318,85 @@ class PartitionedLayer(torch.autograd.Function):
         return gx, g_wtop, g_wqv, (ga if ctx.needs_input_grad[3] else None), gbias, None, None, None
 
 
-def layer_partitioned(chs, x_local, part, training=None, kernels=None):
+def _edis_agg_kernels():
+    """(forward, backward) of the shared-operand (aggregate-then-project) layer on raw operands."""
+    from . import functional as Fn
+
+    def fwd(graph, d, P, Q, X, a, want_sign):
+        return Fn.sage_forward_raw(graph, d, Fn._ptr(P), P.stride(0), Fn._ptr(Q), Q.stride(0), X, a, want_sign)
+
+    def bwd(graph, d, P, Q, X, a, saved, g_agg, g_edge_e, need_gx):
+        agg, edge_e, stats, esign = saved
+        gP = torch.empty_like(P)
+        gQ = torch.empty_like(Q)
+        ga = torch.zeros(d.C, d.D, dtype=torch.float32, device=P.device)
+        gX = Fn.sage_backward_raw(graph, d, Fn._ptr(P), P.stride(0), Fn._ptr(Q), Q.stride(0), X, a, agg, edge_e, stats,
+                                  esign, g_agg, g_edge_e, Fn._ptr(gP), gP.stride(0), Fn._ptr(gQ), gQ.stride(0), ga,
+                                  need_gx)
+        return gP, gQ, ga, gX
+
+    return fwd, bwd
+
+
+class PartitionedAggLayer(torch.autograd.Function):
+    """Layer 2 of DISGAT (F == D == 64) on a partition as AGGREGATE-THEN-PROJECT (att 3, gnn_type AT / GCN):
+    (sum_j a_ij x_j) W_em == sum_j a_ij (x_j W_em), so only the SCORE operand Q is projected for the own + halo
+    source rows (C*D columns instead of 2*C*D) and the value projection W_em runs on the rank's OWN rows
+    (functional.ChannelLinear, outside this node).  The projection GEMMs over source rows are what does not
+    shrink with the rank count on a graph without locality; this halves them for the layer.
+
+      forward   exchange x_local  ||  P = x_local W_top  ->  Q = x_src W_bot  ->  shared-operand kernel
+                -> agg[n_local, C*F] = sum_j alpha_ij x_j per channel
+      backward  kernels -> gP[n_local], gQ[n_src], gX_src[n_src, F] (aggregation part, from the source pass)
+                -> dX_src = gX_src + gQ W_bot^T  -> reverse exchange  ||  dW GEMMs + own-row part."""
+
+    @staticmethod
+    def forward(ctx, x_local, w_top, w_bot, a, part, desc, kernels):
+        from .functional import phase
+        pend = start_source_gather(x_local, part)
+        with phase("gemm_fwd"):
+            P = _project(x_local, w_top)
+        with phase("exchange_exposed"):
+            x_src = pend.wait().contiguous()
+        with phase("gemm_fwd"):
+            Q = _project(x_src, w_bot)
+        a_c = a.contiguous()
+        agg, edge_e, stats, esign = kernels[0](part.graph, desc, P, Q, x_src, a_c, True)
+        ctx.part, ctx.desc, ctx.kernels = part, desc, kernels
+        ctx.save_for_backward(x_local, x_src, w_top, w_bot, a_c, P, Q, agg, edge_e, stats, esign)
+        ctx.set_materialize_grads(False)
+        return agg, edge_e
+
+    @staticmethod
+    def backward(ctx, g_agg, g_edge_e):
+        from .functional import _xt_g, phase
+        x_local, x_src, w_top, w_bot, a, P, Q, agg, edge_e, stats, esign = ctx.saved_tensors
+        part, d = ctx.part, ctx.desc
+        if g_agg is None:
+            g_agg = torch.zeros_like(agg)
+        g_agg = g_agg.contiguous()
+        if g_edge_e is not None:
+            g_edge_e = g_edge_e.contiguous()
+        need_gx = ctx.needs_input_grad[0]
+        gP, gQ, ga, gX_src = ctx.kernels[1](part.graph, d, P, Q, x_src, a, (agg, edge_e, stats, esign), g_agg, g_edge_e,
+                                            need_gx)
+        del P, Q, agg, edge_e, stats, esign
+        pend = None
+        with phase("gemm_bwd"):
+            if need_gx:
+                pend = start_source_scatter(torch.addmm(gX_src, gQ, w_bot.t()), part)
+            g_wbot = _xt_g(x_src, gQ) if ctx.needs_input_grad[2] else None
+            g_wtop = _xt_g(x_local, gP) if ctx.needs_input_grad[1] else None
+            gx_own = gP @ w_top.t() if need_gx else None
+        gx = None
+        if need_gx:
+            with phase("exchange_exposed"):
+                gx = pend.wait()
+            gx = gx + gx_own
+        return gx, g_wtop, g_wbot, (ga if ctx.needs_input_grad[3] else None), None, None, None
+
+
+def layer_partitioned(chs, x_local, part, training=None, kernels=None, agg_kernels=None):
     """C DisGALayer channels on this rank's rows: -> out[n_local, C*D] (= cat_c elu(h'_c)), edge_e."""
     from . import _lib
     from .layers import _next_seed
@@ -340,10 +418,23 @@ def layer_partitioned(chs, x_local, part, training=None, kernels=None):
     # the rank is folded into the seed: ranks hash LOCAL edge ids and must not draw identical masks
     seed = (_next_seed() + 0x632BE59BD9B4E019 * (part.rank + 1)) & (2 ** 64 - 1) if (training and p > 0) else 0
     desc = _lib.LayerDesc(att=att, C=C, D=D, Dv=D, training=1 if (training and p > 0) else 0, p=float(p), seed=seed)
+    # aggregate-then-project where the shared operand has the 128-bit layout (F == D == 64, C in {2, 4, 8}: DISGAT's
+    # second layer) and there is more than one rank: halves the source-row projection GEMMs (EDIS_PART_PLAN=proj: off)
+    plan = os.environ.get("EDIS_PART_PLAN", "auto")
+    if agg_kernels is not None or (plan != "proj" and kernels is None and part.world > 1 and Fin == D == 64
+                                   and C in (2, 4, 8)) or plan == "agg":
+        from .functional import ChannelLinear
+        desc.Dv = Fin
+        desc.flags = _lib.FLAG_PLAIN_MEAN | (0 if x_local.requires_grad else _lib.FLAG_NO_GX)
+        w_bot = torch.cat([l.W[Fin:] for l in chs], 1)
+        agg, edge_e = PartitionedAggLayer.apply(x_local, w_top, w_bot, a, part, desc, agg_kernels or _edis_agg_kernels())
+        w_em = torch.stack([(l.W_em if gnn == "AT" else l.ag_layer.weight) for l in chs], 0)      # [C, F, D]
+        h = ChannelLinear.apply(agg, w_em)
+        return F.elu(h + bias if bias is not None else h), edge_e
     return PartitionedLayer.apply(x_local, w_top, w_qv, a, bias, part, desc, kernels or _edis_kernels())
 
 
-def get_em_partitioned(enc, fusers, x_local, part, layer_fn=None, kernels=None):
+def get_em_partitioned(enc, fusers, x_local, part, layer_fn=None, kernels=None, agg_kernels=None):
     """`DISGAT.get_em` (models.py:217-252) over a destination-range partition: returns this
     rank's rows of [feature_1, feature_2].  layer_fn(chs, x_src, graph) -> out replaces the whole layer
     after a plain SourceExchange (round-1 test hook); kernels = (fwd, bwd) replaces only the fused
@@ -354,7 +445,9 @@ def get_em_partitioned(enc, fusers, x_local, part, layer_fn=None, kernels=None):
         if layer_fn is not None:
             out = layer_fn(chs, SourceExchange.apply(x, part), part.graph)
         else:
-            out = layer_partitioned(chs, x, part, kernels=kernels)[0]
+            # agg_kernels (test hook) selects the aggregate-then-project node for the layers it applies to
+            ak = agg_kernels if (agg_kernels is not None and chs[0].in_features == chs[0].out_features) else None
+            out = layer_partitioned(chs, x, part, kernels=kernels, agg_kernels=ak)[0]
         fused = enc._fuse(layer, fusers, out, x)
         x = F.dropout(fused, enc.dropout, training=enc.training)
         feats.append(x)

@@ -154,7 +154,38 @@ def oracle_kernels(part):
     return fwd, bwd
 
 
-def layer_worker(rank, world, port, out_q, mode, gnn):
+def oracle_agg_kernels(part):
+    """(fwd, bwd) of the shared-operand (aggregate-then-project) kernels for parallel.PartitionedAggLayer, in
+    plain torch: agg[i, c, :] = sum_j alpha^c_ij x_j with alpha from a . lrelu(P_i + Q_j)."""
+    row = torch.from_numpy(part.row_local)
+    col = torch.from_numpy(part.col_local)
+
+    def forward(P, Q, X, a, C, D):
+        z = P[row] + Q[col]
+        e = (torch.nn.functional.leaky_relu(z, 0.01).reshape(-1, C, D) * a.reshape(1, C, D)).sum(-1)
+        w = torch.exp(torch.sigmoid(e))
+        alpha = w / torch.zeros(part.n_local, C).index_add_(0, row, w)[row]
+        msg = alpha.unsqueeze(-1) * X[col].unsqueeze(1)                               # [E, C, F]
+        agg = torch.zeros(part.n_local, C, X.shape[1]).index_add_(0, row, msg)
+        return agg.reshape(part.n_local, -1), e
+
+    def fwd(graph, d, P, Q, X, a, want_sign):
+        with torch.no_grad():
+            agg, e = forward(P, Q, X, a, d.C, d.D)
+        return agg, e, None, None
+
+    def bwd(graph, d, P, Q, X, a, saved, g_agg, g_edge_e, need_gx):
+        leaves = [t.detach().requires_grad_(True) for t in (P, Q, a, X)]
+        with torch.enable_grad():
+            agg, e = forward(leaves[0], leaves[1], leaves[3], leaves[2], d.C, d.D)
+            tot = (agg * g_agg).sum() + (0 if g_edge_e is None else (e * g_edge_e).sum())
+        gP, gQ, ga, gX = torch.autograd.grad(tot, leaves)
+        return gP, gQ, ga, (gX if need_gx else None)
+
+    return fwd, bwd
+
+
+def layer_worker(rank, world, port, out_q, mode, gnn, agg=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), EDIS_EXCHANGE=mode)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
@@ -163,7 +194,8 @@ def layer_worker(rank, world, port, out_q, mode, gnn):
         part = par.partition_of_global_graph(idx, n, rank, world)
         assert part.mode == mode
         x_loc = x[part.lo:part.hi].clone().requires_grad_(True)
-        feats = par.get_em_partitioned(enc, fus, x_loc, part, kernels=oracle_kernels(part))
+        feats = par.get_em_partitioned(enc, fus, x_loc, part, kernels=oracle_kernels(part),
+                                       agg_kernels=oracle_agg_kernels(part) if agg else None)
         (feats[-1] * R[part.lo:part.hi]).sum().backward()
         params = [p for m in [enc] + fus for p in m.parameters()]
         par.allreduce_grads(params)
@@ -174,15 +206,20 @@ def layer_worker(rank, world, port, out_q, mode, gnn):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("mode,gnn,world", [("allgather", "AT", 2), ("alltoall", "AT", 2), ("allgather", "GCN", 3)])
-def test_partitioned_layer_node_matches_single_process(mode, gnn, world):
+@pytest.mark.parametrize("mode,gnn,world,agg", [("allgather", "AT", 2, False), ("alltoall", "AT", 2, False),
+                                                ("allgather", "GCN", 3, False), ("allgather", "AT", 2, True),
+                                                ("alltoall", "GCN", 2, True)])
+def test_partitioned_layer_node_matches_single_process(mode, gnn, world, agg):
     """parallel.PartitionedLayer (own-row P, own+halo Q|V, overlapped exchange, hand-ordered backward)
     through both exchange collectives: features, INPUT gradient and weight gradients equal the
-    single-process run of the same oracle kernels."""
+    single-process run of the same oracle kernels.  agg=True: layer 2 (F == D) runs as
+    parallel.PartitionedAggLayer (aggregate-then-project: only Q projected for halo rows, W_em on own rows);
+    the single-process comparison always uses the project-then-aggregate node, so the two plans are also
+    checked against each other."""
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = free_port()
-    procs = [ctx.Process(target=layer_worker, args=(r, world, port, q, mode, gnn)) for r in range(world)]
+    procs = [ctx.Process(target=layer_worker, args=(r, world, port, q, mode, gnn, agg)) for r in range(world)]
     for p in procs:
         p.start()
     results = dict(q.get(timeout=180) for _ in range(world))
