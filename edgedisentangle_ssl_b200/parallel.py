@@ -418,11 +418,13 @@ def layer_partitioned(chs, x_local, part, training=None, kernels=None, agg_kerne
     # the rank is folded into the seed: ranks hash LOCAL edge ids and must not draw identical masks
     seed = (_next_seed() + 0x632BE59BD9B4E019 * (part.rank + 1)) & (2 ** 64 - 1) if (training and p > 0) else 0
     desc = _lib.LayerDesc(att=att, C=C, D=D, Dv=D, training=1 if (training and p > 0) else 0, p=float(p), seed=seed)
-    # aggregate-then-project where the shared operand has the 128-bit layout (F == D == 64, C in {2, 4, 8}: DISGAT's
-    # second layer) and there is more than one rank: halves the source-row projection GEMMs (EDIS_PART_PLAN=proj: off)
-    plan = os.environ.get("EDIS_PART_PLAN", "auto")
-    if agg_kernels is not None or (plan != "proj" and kernels is None and part.world > 1 and Fin == D == 64
-                                   and C in (2, 4, 8)) or plan == "agg":
+    # EDIS_PART_PLAN=agg: aggregate-then-project (PartitionedAggLayer) -- halves the source-row projection GEMMs of
+    # a layer with F == D == 64.  Measured on config A (profiles/r2_bench_n2_layer2_agg_plan.json, N = 2): GEMMs
+    # 42.4 -> 33.4 ms, but the shared-operand kernels have no ring variant (+7 ms) and the per-channel W_em GEMMs +
+    # ELU run as separate passes over the own rows (+12 ms): 142.6 -> 153.0 ms.  At 8 ranks the own rows are 4x
+    # fewer and the estimate is break-even, so project-then-aggregate stays the default.
+    plan = os.environ.get("EDIS_PART_PLAN", "proj")
+    if agg_kernels is not None or plan == "agg":
         from .functional import ChannelLinear
         desc.Dv = Fin
         desc.flags = _lib.FLAG_PLAIN_MEAN | (0 if x_local.requires_grad else _lib.FLAG_NO_GX)

@@ -18,7 +18,8 @@ max(2e-5, 4 x the single-GPU run's own error on that tensor, the single-GPU run'
 tensors) of the float64 arbiter, measured against the tensor's max -- i.e. the partitioned run must be as
 close to the true gradient as the single-GPU run is (this objective is ill-conditioned on purpose: the
 single-GPU fp32 gradient itself is ~1e-3 from the float64 one on its worst tensor).
-Both exchange collectives (all-gather / all-to-all) are exercised.  Prints one JSON line; exit code 1 on failure."""
+Both exchange collectives (all-gather / all-to-all) and the optional aggregate-then-project plan of layer 2
+(parallel.PartitionedAggLayer) are exercised.  Prints one JSON line; exit code 1 on failure."""
 import json
 import os
 import sys
@@ -65,8 +66,9 @@ def main():
     params = [p for m in [enc] + fus for p in m.parameters()]
 
     results = {}
-    for mode in ("allgather", "alltoall"):
-        os.environ["EDIS_EXCHANGE"] = mode
+    for mode in ("allgather", "alltoall", "allgather+agg"):
+        os.environ["EDIS_EXCHANGE"] = mode.split("+")[0]
+        os.environ["EDIS_PART_PLAN"] = "agg" if mode.endswith("+agg") else "proj"   # layer 2 aggregate-then-project
         part = par.partition_of_global_graph(idx, n, rank, world, device=dev)
         lo, hi = part.lo, part.hi
         mine = (key // n >= lo) & (key // n < hi)

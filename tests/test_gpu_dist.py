@@ -34,5 +34,5 @@ def test_partitioned_path_over_nccl_matches_single_gpu_and_f64(world):
     assert lines, p.stderr[-3000:]
     rep = json.loads(lines[-1])
     assert p.returncode == 0 and rep["ok"], rep
-    for mode in ("allgather", "alltoall"):
-        assert rep["modes"][mode]["exchange"] == mode and rep["modes"][mode]["ok"]
+    for mode in ("allgather", "alltoall", "allgather+agg"):
+        assert rep["modes"][mode]["exchange"] == mode.split("+")[0] and rep["modes"][mode]["ok"]
