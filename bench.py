@@ -557,7 +557,8 @@ def main():
                 "plan": plan, "kernels": per}
         tpath = os.path.join(ROOT, "profiles", "traffic.json")
         if os.path.exists(tpath) and world == 1 and a.config == "A":
-            roof["traffic"] = json.load(open(tpath)).get(dom)
+            tj = json.load(open(tpath))
+            roof["traffic"] = tj.get(dom) or tj.get(dom + "_ring")       # the ring kernels are the ones config A runs
     step_ms = ms_res / a.steps
     breakdown = {"ms_per_step": step_ms, "sparse_kernels_ms": tot_ms,
                  "projection_gemm_ms": phases.get("gemm_fwd", 0.0) + phases.get("gemm_bwd", 0.0) or None,
