@@ -315,25 +315,40 @@ def _gen_key(a):
     return int.from_bytes(hashlib.blake2b(s.encode(), digest_size=8).digest(), "little")
 
 
-def global_graph_indices(a, rank, world, barrier):
+def global_graph_indices(a, rank, world, dev="cuda"):
     """[2, E] processed adjacency of the ONE bench graph, generated once per box (rank 0) and shared
-    with the other ranks / later runs through the cache directory as a memory-mapped .npy."""
+    with the other ranks / later runs through the cache directory as a memory-mapped .npy.
+    Every decision that changes which collectives run is taken by rank 0 and broadcast, so ranks that
+    arrive at different times cannot take different branches."""
     from edgedisentangle_ssl_b200.synthetic import power_law_graph
     path = os.path.join(a.cache_dir, "coo_%016x.npy" % _gen_key(a)) if a.cache_dir else None
-    if path and os.path.exists(path):
+
+    def agree(value):
+        if world == 1:
+            return value
+        import torch.distributed as dist
+        flag = torch.tensor([1 if value else 0], device=dev)
+        dist.broadcast(flag, 0)
+        return bool(int(flag.item()))
+
+    if agree(bool(path) and os.path.exists(path)):
         return np.load(path, mmap_mode="r"), True
     idx = None
-    if rank == 0 or not path:
+    saved = False
+    if rank == 0:
         idx = power_law_graph(a.nodes, a.raw_edges, seed=0)
         if path:
-            os.makedirs(a.cache_dir, exist_ok=True)
-            tmp = path + ".tmp%d.npy" % os.getpid()
-            np.save(tmp, idx)
-            os.replace(tmp, path)
-    if world > 1 and path:
-        barrier()
-        if idx is None:
-            idx = np.load(path, mmap_mode="r")
+            try:                                   # the cache is an optimisation: a read-only tree must not fail the run
+                os.makedirs(a.cache_dir, exist_ok=True)
+                tmp = path + ".tmp%d.npy" % os.getpid()
+                np.save(tmp, idx)
+                os.replace(tmp, path)
+                saved = True
+            except OSError:
+                saved = False
+    saved = agree(saved)                           # also the point where the other ranks wait for rank 0
+    if idx is None:
+        idx = np.load(path, mmap_mode="r") if saved else power_law_graph(a.nodes, a.raw_edges, seed=0)
     return idx, False
 
 
@@ -378,10 +393,13 @@ def main():
         graph = edis.Graph.load(gpath, _gen_key(a), dev, a.max_chunk) if gpath else None
         cache_hit = graph is not None
         if graph is None:
-            idx, _ = global_graph_indices(a, 0, 1, barrier)
+            idx, _ = global_graph_indices(a, 0, 1, dev)
             graph = edis.Graph(a.nodes, idx[0], idx[1], device=dev, max_chunk=a.max_chunk)
             if gpath:
-                graph.save(gpath, _gen_key(a))
+                try:
+                    graph.save(gpath, _gen_key(a))
+                except Exception:                  # read-only tree: run without the cache
+                    pass
             del idx
         n_local, n_total, e_local, lo = a.nodes, a.nodes, graph.e, 0
     elif strong and a.config == "B":
@@ -398,7 +416,7 @@ def main():
         graph, n_local, e_local, lo = part.graph, part.n_local, part.graph.e, part.lo
     elif strong:
         n_total = a.nodes
-        idx, cache_hit = global_graph_indices(a, rank, world, barrier)
+        idx, cache_hit = global_graph_indices(a, rank, world, dev)
         part = par.partition_of_global_graph(idx, n_total, rank, world, device=dev, max_chunk=a.max_chunk)
         del idx
         graph, n_local, e_local, lo = part.graph, part.n_local, part.graph.e, part.lo

@@ -380,3 +380,44 @@ def test_partition_sampler_rows_and_labels():
     assert n_pos >= pos_key.numel() // 3                                    # the forced third is inside
     expect = 3.0 * pos_key.numel() + pos_key.numel() / 3.0                  # E[M] ~ 3E + E/3 (minus overlap)
     assert 0.8 * expect < m < 1.1 * expect
+
+
+# ------------------------------------------------------------------ bench.py: sharing the generated graph between ranks
+def graph_share_worker(rank, world, port, out_q, cache_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import argparse
+        import importlib.util
+        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+        bench = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(bench)
+        a = argparse.Namespace(nodes=3000, raw_edges=20000, max_chunk=0, cache_dir=cache_dir)
+        idx, hit = bench.global_graph_indices(a, rank, world, "cpu")
+        idx2, hit2 = bench.global_graph_indices(a, rank, world, "cpu")          # second call: cache hit if writable
+        out_q.put((rank, (np.asarray(idx).copy(), bool(hit), np.asarray(idx2).copy(), bool(hit2))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("writable", [True, False])
+def test_bench_graph_is_shared_consistently_between_ranks(tmp_path, writable):
+    """bench.global_graph_indices: rank 0 generates and publishes the graph, the other ranks wait on a broadcast
+    and map the file -- or, when the cache directory cannot be written, every rank generates it from the same
+    seed.  Both ranks must end up with identical arrays and take identical collective branches (no hang)."""
+    cache = str(tmp_path / "cache") if writable else "/proc/edis-not-writable"
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = free_port()
+    procs = [ctx.Process(target=graph_share_worker, args=(r, world, port, q, cache)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][2], res[1][2]) and np.array_equal(res[0][0], res[0][2])
+    assert res[0][1] is False and res[1][1] is False
+    assert res[0][3] == res[1][3] == writable
