@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-budget-s", type=float, default=12.0, help="cpu_baseline leg: seconds per reference step")
     ap.add_argument("--ref-total-s", type=float, default=200.0, help="--impl reference: budget of the whole run")
+    ap.add_argument("--cpu-probe-edges", type=int, default=250_000, help="CPU arm: edges of the calibration sample")
     ap.add_argument("--max-chunk", type=int, default=0)
     ap.add_argument("--no-epoch-metric", action="store_true", help="skip the cora_full epoch-ms secondary metric")
     ap.add_argument("--no-ssl-metric", action="store_true", help="skip the SupEdge step secondary metric")
@@ -105,7 +106,8 @@ def cpu_reference_leg(a, step_budget_s, steps, warmup, threads):
     bounded power-law sample sized for ~`step_budget_s` seconds per step (oracle.ref_arm.sized_workload:
     E = 2M doubling, BASELINE.md section 4, or smaller when 2M does not fit the budget)."""
     from oracle import ref_arm
-    wl, _ = ref_arm.sized_workload(a.feat, a.nhead, a.nhid, a.att, a.gnn_type, a.dropout, threads, step_budget_s)
+    wl, _ = ref_arm.sized_workload(a.feat, a.nhead, a.nhid, a.att, a.gnn_type, a.dropout, threads, step_budget_s,
+                                   probe_edges=a.cpu_probe_edges)
     for _ in range(max(warmup, 1)):
         wl.step()
     times = [wl.step() for _ in range(max(steps, 1))]
